@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the RPBCAC training hot path (BASELINE.json metric: agent-updates/sec).
+
+  python bench.py --gpus 1 --steps K --warmup W              our arm (B200 kernels)
+  python bench.py --impl reference --gpus N --steps K ...    CPU arm: the oracle port of the reference on host cores
+  torchrun ... bench.py --gpus N ...                         one rank per GPU, env batch sharded (weak scaling)
+
+A "step" is one fixed-policy block of the training loop over one batch of synthetic environments:
+rollout of n_ep_fixed x max_ep_len steps for n_envs environments x n_agents agents, followed by the full
+update round (Phases I-IV, training/train_agents.py:86-163) at the steady-state buffer (buffer_size + one block).
+agent-updates per step = n_agents * n_envs * max_ep_len * n_ep_fixed.
+
+Workload (config.workload = "C2"): BASELINE.json configs[1] -- 5x5 grid, 4 cooperative + 1 malicious agent,
+H = 1, 4096 parallel environments per GPU, reference hyper-parameters (main.py:31-40, slow_lr 0.002).
+Inputs are larger than L2 (steady-state buffer 1.47 GB >> 126 MB), so no explicit L2 flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+DROPIN = os.path.join(ROOT, "resilient-consensus-based-marl_b200")
+for p in (ROOT, DROPIN):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+IN_NODES5 = [[0, 1, 2, 3], [1, 2, 3, 4], [2, 3, 4, 0], [3, 4, 0, 1], [4, 0, 1, 2]]
+HYPER = dict(gamma=0.9, fast_lr=0.01, slow_lr=0.002, max_ep_len=20, n_ep_fixed=50, n_epochs=10, buffer_size=2000)
+
+
+def load_pretrained(tag="malicious_H1_s100"):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "kat_est_returns.npz"))
+    w = []
+    for i in range(5):
+        nets, n = [], 0
+        while f"{tag}/agent{i}/n{n}_k0" in z.files:
+            nets.append([z[f"{tag}/agent{i}/n{n}_k{k}"] for k in range(6)])
+            n += 1
+        w.append(nets)
+    return w, z[f"{tag}/desired"], [str(x) for x in z[f"{tag}/labels"]]
+
+
+def workload(name, n_envs):
+    if name == "C2":
+        w, desired, labels = load_pretrained()
+        return dict(labels=labels, in_nodes=IN_NODES5, weights=w, desired=desired, nrow=5, ncol=5, H=1,
+                    n_envs=n_envs or 4096, **HYPER)
+    if name == "C1":
+        w, desired, _ = load_pretrained()
+        return dict(labels=["Cooperative"] * 5, in_nodes=IN_NODES5, weights=w, desired=desired, nrow=5, ncol=5, H=0,
+                    n_envs=n_envs or 1, **HYPER)
+    if name == "C3":
+        from rcmarl import nets
+        rs = np.random.RandomState(0)
+        NA = 16
+        w = [[nets.glorot_uniform(32, 5, rs), nets.glorot_uniform(32, 1, rs), nets.glorot_uniform(48, 1, rs)] for _ in range(NA)]
+        desired = np.random.RandomState(300).randint(0, 10, size=(NA, 2))
+        in_nodes = [[(i + k) % NA for k in range(6)] for i in range(NA)]
+        return dict(labels=["Cooperative"] * NA, in_nodes=in_nodes, weights=w, desired=desired, nrow=10, ncol=10, H=2,
+                    n_envs=n_envs or 8192, **HYPER)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, sm_max_mhz=1965.0), "fallback"
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(cfg, rounds, seed=0):
+    """The oracle port of the reference loop (oracle/rpbcac_oracle.py) on the host cores: N = 1 environment
+    (the reference is single-environment), same agents / hyper-parameters / schedule as the GPU arm.
+    Returns (agent_updates_per_s, seconds, description)."""
+    from oracle import rpbcac_oracle as O
+    labels, w = cfg["labels"], cfg["weights"]
+    NA = len(labels)
+    agents = []
+    for i, l in enumerate(labels):
+        a, c, t = w[i][0], w[i][1], w[i][2]
+        if l == "Malicious":
+            agents.append(O.MaliciousOracleAgent(a, c, t, cfg["slow_lr"], cfg["fast_lr"], cfg["gamma"], critic_local_w=w[i][3]))
+        else:
+            agents.append(O.RPBCACOracleAgent(a, c, t, cfg["slow_lr"], cfg["fast_lr"], cfg["gamma"], H=cfg["H"]))
+    env = O.GridWorldOracle(cfg["nrow"], cfg["ncol"], NA, cfg["desired"], n_envs=1)
+    rs = np.random.RandomState(seed)
+    perm_source = O.make_perm_source(seed + 1)
+    n_ep, Lq = cfg["n_ep_fixed"], cfg["max_ep_len"]
+    S = NS = A = R = None
+    # steady-state buffer: two untimed blocks first
+    def block():
+        init = rs.randint(0, cfg["nrow"], size=(n_ep, 1, NA, 2))
+        U = rs.rand(n_ep, Lq, 1, NA, 3).astype(np.float32)
+        return O.rollout_block(env, agents, labels, n_episodes=n_ep, max_ep_len=Lq, gamma=cfg["gamma"], init_states=init, uniforms=U)
+    for _ in range(2):
+        s, ns, a, r, _e, _r = block()
+        S, NS, A, R = (s, ns, a, r) if S is None else tuple(np.concatenate(p) for p in ((S, s), (NS, ns), (A, a), (R, r)))
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        s, ns, a, r, _e, _r = block()
+        S, NS, A, R = tuple(np.concatenate(p) for p in ((S, s), (NS, ns), (A, a), (R, r)))
+        O.update_round(agents, labels, cfg["in_nodes"], S, NS, A, R, n_envs=1, n_epochs=cfg["n_epochs"],
+                       n_actor_steps=n_ep * Lq, common_reward=False, perm_source=perm_source)
+        keep = cfg["buffer_size"]
+        S, NS, A, R = S[-keep:], NS[-keep:], A[-keep:], R[-keep:]
+    dt = time.perf_counter() - t0
+    upd = NA * 1 * Lq * n_ep * rounds
+    return upd / dt, dt, f"{rounds} update round(s) of the oracle loop at n_envs=1 (reference shape), {upd} agent-updates"
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--n-envs", type=int, default=0, help="environments PER GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-consensus", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    cfg = workload(args.workload, args.n_envs)
+    NA, N = len(cfg["labels"]), cfg["n_envs"]
+    upd_per_step = NA * N * cfg["max_ep_len"] * cfg["n_ep_fixed"]
+    config = dict(workload=args.workload, grid=f"{cfg['nrow']}x{cfg['ncol']}", n_agents=NA, labels=cfg["labels"], H=cfg["H"],
+                  n_envs_per_gpu=N, n_envs_total=N * world, steps_per_block=cfg["max_ep_len"] * cfg["n_ep_fixed"],
+                  n_epochs=cfg["n_epochs"], buffer_time_rows=cfg["buffer_size"] + cfg["max_ep_len"] * cfg["n_ep_fixed"],
+                  l2="inputs larger than L2 (no flush needed)", parallelism=f"dp{world}")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ncores = os.cpu_count()
+        import torch
+        torch.set_num_threads(ncores)
+        vals = []
+        for _ in range(max(args.warmup, 0) and 0):
+            pass
+        t_all = time.perf_counter()
+        for _ in range(args.steps):
+            v, dt, desc = cpu_reference_arm(cfg, rounds=1)
+            vals.append(v)
+        v = float(np.mean(vals))
+        line = dict(metric="agent-updates/sec", value=v, unit="agent-updates/s", n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=1000.0 * (time.perf_counter() - t_all) / max(args.steps, 1),
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    impl="reference", config=config,
+                    cpu_baseline=dict(value=v, unit="agent-updates/s", cores=ncores, kind="port",
+                                      sample=desc + " per step; NumPy (BLAS threads = all cores) restatement of the "
+                                      "reference loop -- faster than the original TF-2.4 code path (no Keras retracing)"),
+                    e2e=dict(value=v, unit="agent-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from rcmarl.trainer import Trainer
+    from rcmarl import ops, _lib
+
+    tr = Trainer(rank=rank, world=world, group=group, seed=1234, **cfg)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # steady-state buffer (3 rounds in): two untimed blocks, no update
+    tr.rollout_block()
+    tr.rollout_block()
+
+    def step():
+        tr.rollout_block()
+        tr.update_round()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    tr.profile = {}
+    l0 = tr.launches
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clk = clocks.stop() if rank == 0 else {}
+    launches = tr.launches - l0
+    prof = {k: [a.elapsed_time(b) for a, b in v] for k, v in tr.profile.items()}
+    tr.profile = None
+    value = upd_per_step * world * args.steps / (ms / 1000.0)
+
+    # ---- roofline of the dominant kernel: the fused fwd/bwd gradient kernel of the full-batch fits
+    peaks, peak_kind = measured_peaks()
+    rows = tr.t_filled * N if tr.t_filled else 0
+    rows_fit = (cfg["buffer_size"] + cfg["max_ep_len"] * cfg["n_ep_fixed"]) * N
+    n_coop = sum(l == "Cooperative" for l in cfg["labels"])
+    fit_ms = float(np.mean(prof["fit_grad"])) if prof.get("fit_grad") else None
+    roof = None
+    if fit_ms:
+        alg_bytes = 20 * NA * rows_fit                       # 20*n_agents B per row per lock-step GD step
+        d_c, d_t = 2 * NA, 3 * NA
+        mac = n_coop * ((d_c * 20 + 400 + 20) + (d_c * 20 + 400 + 20 + 400 + 20 + 20) +
+                        (d_t * 20 + 400 + 20) + (d_t * 20 + 400 + 20 + 400 + 20 + 20))
+        flops = 2.0 * mac * rows_fit
+        fp32_peak = 2 * 128 * 148 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+        roof = dict(kernel="grad_kernel<5,MSE> (rcmarl_grad, full-batch fit step)", bound="hbm",
+                    achieved=alg_bytes / (fit_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=alg_bytes / (fit_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=None,
+                    peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", ms_per_launch=fit_ms,
+                    launches_timed=len(prof["fit_grad"]), algorithmic_bytes_per_launch=alg_bytes,
+                    note="this kernel is FP32-FMA bound (350 FLOP/B); see fp32",
+                    fp32=dict(achieved=flops / (fit_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
+                              frac=flops / (fit_ms * 1e-3) / 1e12 / fp32_peak,
+                              peak_source="nominal 2*128 lanes*148 SMs*max SM clock (no measured FP32 peak provided)",
+                              algorithmic_flop_per_launch=flops))
+    breakdown = {k: dict(ms_total=float(np.sum(v)), calls=len(v)) for k, v in prof.items()}
+
+    # ---- consensus microbench (BASELINE metric part 2, C5): 64 x 1M clip-mean, HBM-bound
+    cons = None
+    if rank == 0 and not args.no_consensus:
+        g = torch.Generator(device="cuda")
+        g.manual_seed(0)
+        X = torch.randn(64, 1 << 20, device="cuda", generator=g)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+        out = torch.empty(1 << 20, device="cuda")
+        cons = {}
+        for H in (0, 1, 4):
+            for _ in range(3):
+                ops.clip_mean(X, H, out)
+            ts = []
+            for _ in range(10):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); ops.clip_mean(X, H, out); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            t = float(np.median(ts))
+            gbs = 4.0 * (1 << 20) * 65 / (t * 1e-3) / 1e9
+            cons[f"H={H}"] = dict(ms=t, achieved=gbs, unit="GB/s", frac=gbs / peaks["hbm_gbs"])
+        cons["algorithmic_bytes"] = 4 * (1 << 20) * 65
+        cons["peak"] = peaks["hbm_gbs"]
+        cons["l2"] = "256 MiB flush write between timed launches"
+        del X, flush
+
+    # ---- e2e: the reference-facing API (training.train_agents.train_RPBCAC) with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_arm(cfg, args, rank, world, tr)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, dt, desc = cpu_reference_arm(cfg, rounds=2)
+        cpu = dict(value=v, unit="agent-updates/s", cores=os.cpu_count(), kind="port", seconds=dt,
+                   sample=desc + "; NumPy restatement of the reference loop (oracle/rpbcac_oracle.py), faster than the "
+                   "original TF-2.4 path")
+
+    if rank == 0:
+        line = dict(metric="agent-updates/sec", value=value, unit="agent-updates/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", config=config, clocks=clk, e2e=e2e,
+                    gpu_launches=launches, roofline=roof, consensus_roofline=cons, cpu_baseline=cpu,
+                    breakdown_ms=breakdown, update_rounds_per_s=args.steps / (ms / 1000.0))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def e2e_arm(cfg, args, rank, world, tr):
+    """Same metric through the public, reference-shaped API with HOST buffers: agents are built from host (NumPy)
+    weights, the steady-state replay buffer is handed over as host arrays (exp_buffer, train_agents.py:36-40),
+    train_RPBCAC runs `steps` blocks and returns host weights + the sim_data frame.  Host->device copies of the
+    buffer / weights / permutations and device->host reads of logs, losses and weights are inside the timed region."""
+    import torch
+    try:
+        import training.train_agents as training
+        from rcmarl import api
+    except Exception as ex:                                   # pragma: no cover
+        return dict(value=None, unit="agent-updates/s", error=f"public API unavailable: {ex!r}")
+    NA, N = len(cfg["labels"]), cfg["n_envs"]
+    keep = cfg["buffer_size"] * N
+    host = api.export_buffer(tr, keep)                        # pinned host copies of the newest buffer_size time rows
+    n_steps = args.steps
+    res = api.timed_train(cfg, host, n_blocks=n_steps, rank=rank, world=world)
+    upd = NA * N * cfg["max_ep_len"] * cfg["n_ep_fixed"] * n_steps * world
+    return dict(value=upd / res["seconds"], unit="agent-updates/s", h2d_bytes_per_step=res["h2d_bytes"] // n_steps,
+                d2h_bytes_per_step=res["d2h_bytes"] // n_steps, seconds=res["seconds"],
+                api="training.train_agents.train_RPBCAC(env, agents, args, exp_buffer=host arrays)")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

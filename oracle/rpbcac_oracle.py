@@ -414,12 +414,12 @@ class MaliciousOracleAgent:
     action_probs = RPBCACOracleAgent.action_probs
     get_action = RPBCACOracleAgent.get_action
 
-    def actor_update(self, s, ns, r_local, a_local, perm):              # :102-119
+    def actor_update(self, s, ns, r_local, a_local, perm, batch_size=200):   # :102-119
         dt = self.dtype
         V = mlp_forward(self.critic_local_weights, self._f(s))
         nV = mlp_forward(self.critic_local_weights, self._f(ns))
         td = self._c(r_local) + dt(self.gamma) * nV - V
-        self.actor, loss = actor_fit_minibatch(self.actor, self.adam, self._f(s), a_local, td, 200, perm)
+        self.actor, loss = actor_fit_minibatch(self.actor, self.adam, self._f(s), a_local, td, batch_size, perm)
         return loss
 
     def critic_update_compromised(self, s, ns, r_comp, perms, batch_size=32):  # :121-135
@@ -461,12 +461,12 @@ class GreedyOracleAgent:
     action_probs = RPBCACOracleAgent.action_probs
     get_action = RPBCACOracleAgent.get_action
 
-    def actor_update(self, s, ns, r_local, a_local, perm):              # :211-226
+    def actor_update(self, s, ns, r_local, a_local, perm, batch_size=200):   # :211-226
         dt = self.dtype
         V = mlp_forward(self.critic, self._f(s))
         nV = mlp_forward(self.critic, self._f(ns))
         td = self._c(r_local) + dt(self.gamma) * nV - V
-        self.actor, loss = actor_fit_minibatch(self.actor, self.adam, self._f(s), a_local, td, 200, perm)
+        self.actor, loss = actor_fit_minibatch(self.actor, self.adam, self._f(s), a_local, td, batch_size, perm)
         return loss
 
     def critic_update_local(self, s, ns, r_local, perms, batch_size=32):       # :228-241
@@ -592,7 +592,8 @@ def update_round(agents, labels, in_nodes, s, ns, a, r, *, n_envs, n_epochs, n_a
             actor_loss[node] = agents[node].actor_update(s[-na:], ns[-na:], sa[-na:], a[-na:, node])
         else:
             perm = expand_time_perm(perm_source(min(Ta, T)), n_envs)
-            actor_loss[node] = agents[node].actor_update(s[-na:], ns[-na:], r[-na:, node], a[-na:, node], perm)
+            actor_loss[node] = agents[node].actor_update(s[-na:], ns[-na:], r[-na:, node], a[-na:, node], perm,
+                                                         200 * n_envs)      # Appendix C: 200 time rows x all envs
     return dict(critic_loss=critic_loss, TR_loss=TR_loss, actor_loss=actor_loss)
 
 

@@ -1,0 +1,365 @@
+// grad_kernel.cuh -- fused forward + backward of the 20-wide RPBCAC MLPs over a set of buffer rows
+// (rcmarl_grad, include/rcmarl.h; replaces the fwd/bwd inside critic.fit / TR.fit / actor.train_on_batch,
+// agents/resilient_CAC_agents.py:99,118,136 and adversarial:41,116,133,150,163).
+//
+// The kernel is FP32-FMA work fed from shared memory, and on B200 the shared-memory pipe (one wavefront per
+// clock per SM) is the first limit: measured with ncu (profiles/r01_grad_v1_ncu.md) a warp-uniform LDS.128 costs
+// 2 wavefronts and any other LDS.128 costs 4, while the four FMA pipes retire 4 warp-FFMAs per clock.  Balance
+// therefore needs >= 4 FFMA per wavefront everywhere:
+//   phase 1 (forward + backward-data): every lane carries R = 2 buffer rows, so each broadcast weight quad
+//            (uniform LDS.128, 2 wavefronts) feeds 8 FFMA;
+//   phase 2 (weight gradients = sum over rows of outer products): the per-row activation / delta vectors are
+//            staged in a warp-private shared-memory tile and every lane owns one 8x8 register tile of the
+//            gradient (4 LDS.128 = 16 wavefronts per 64 FFMA); lanes are split into row groups so that
+//            NG x (number of tiles) <= 32 lanes are busy.  Accumulators stay in registers across ALL rows of the
+//            CTA; the output-layer gradient of the scalar nets is accumulated per lane in phase 1.
+// Reductions are fixed-order (lane -> warp -> CTA partial -> reduce_kernel): bitwise reproducible.
+#pragma once
+#include "common.cuh"
+
+namespace rcmarl {
+
+__host__ __device__ constexpr int round8(int n) { return (n + 7) & ~7; }
+
+template <int DIN, int NOUT>
+struct TileLayout {
+    static constexpr bool L3T = (NOUT > 1);             // output-layer gradient through tiles (actor) or per lane
+    static constexpr int LA1 = round8(DIN + 1);         // [x .. , 1, 0 pad]
+    static constexpr int OA1 = 0;
+    static constexpr int OA2 = LA1;                     // [h1(20), 1, 0, 0, 0]
+    static constexpr int OA3 = OA2 + 24;                // [h2(20), 1, 0, 0, 0]   (only if L3T)
+    static constexpr int OD1 = OA3 + (L3T ? 24 : 0);    // delta1 (20) + 4 zeros
+    static constexpr int OD2 = OD1 + 24;                // delta2 (20) + 4 zeros
+    static constexpr int OD3 = OD2 + 24;                // dLoss/dlogits (NOUT) + zeros (only if L3T)
+    static constexpr int RAW = OD3 + (L3T ? 8 : 0);
+    // row stride: odd number of 16-byte units => conflict-free float4 stores within a quarter-warp
+    static constexpr int RS = ((RAW / 4) % 2 == 0) ? RAW + 4 : RAW;
+    static constexpr int NT1 = (LA1 / 8) * 3;
+    static constexpr int NT2 = 9;
+    static constexpr int NT3 = L3T ? 3 : 0;
+    static constexpr int NT = NT1 + NT2 + NT3;          // 8x8 tiles covering all weight gradients
+    static_assert(NT <= 32, "tile count exceeds a warp");
+    static constexpr int NG = 32 / NT;                  // row groups processed concurrently by one warp
+    static constexpr int ROWS = 64;                     // rows per warp chunk (R = 2 per lane)
+
+    __device__ static __forceinline__ void tile_offsets(int t, int& aoff, int& doff) {
+        if (t < NT1) {
+            aoff = OA1 + 8 * (t / 3); doff = OD1 + 8 * (t % 3);
+        } else if (t < NT1 + NT2) {
+            t -= NT1; aoff = OA2 + 8 * (t / 3); doff = OD2 + 8 * (t % 3);
+        } else {
+            t -= NT1 + NT2; aoff = OA3 + 8 * t; doff = OD3;
+        }
+    }
+    // packed-parameter index of element (ii, jj) of tile t, -1 for padding
+    __device__ static __forceinline__ int tile_param(int t, int ii, int jj) {
+        if (t < NT1) {
+            const int i = 8 * (t / 3) + ii, j = 8 * (t % 3) + jj;
+            if (j >= HID) return -1;
+            return i < DIN ? i * HID + j : (i == DIN ? off_b1(DIN) + j : -1);
+        } else if (t < NT1 + NT2) {
+            t -= NT1;
+            const int i = 8 * (t / 3) + ii, j = 8 * (t % 3) + jj;
+            if (j >= HID) return -1;
+            return i < HID ? off_W2(DIN) + i * HID + j : (i == HID ? off_b2(DIN) + j : -1);
+        } else if (t < NT) {
+            t -= NT1 + NT2;
+            const int i = 8 * t + ii, o = jj;
+            if (o >= NOUT) return -1;
+            return i < HID ? off_W3(DIN) + i * NOUT + o : (i == HID ? off_b3(DIN, NOUT) + o : -1);
+        }
+        return -1;
+    }
+};
+
+constexpr int GRAD_SMEM_BUDGET = 226 * 1024;   // one CTA per SM (up to 255 registers per thread)
+
+// warps per CTA: as many 64-row tiles as fit next to the staged weights, at most 8
+template <int DIN, int NOUT>
+constexpr int grad_warps_for() {
+    using L = TileLayout<DIN, NOUT>;
+    const int avail = GRAD_SMEM_BUDGET - 4 * (round4(param_count(DIN, NOUT)) + 16);
+    const int n = avail / (4 * L::ROWS * L::RS);
+    return n > 8 ? 8 : n;
+}
+template <int NA, int LOSS>
+constexpr int grad_warps() {
+    if (LOSS == RCMARL_LOSS_CE) return grad_warps_for<2 * NA, NACT>();
+    const int a = grad_warps_for<3 * NA, 1>(), b = grad_warps_for<2 * NA, 1>();
+    return a < b ? a : b;
+}
+
+struct GradParams {
+    rcmarl_rows rows;
+    rcmarl_grad_job jobs[RCMARL_MAX_JOBS];
+    float* partial;   // [gridDim.y][n_jobs][stride]
+    int32_t n_jobs;
+    int32_t stride;
+};
+
+// z[r][:] = b + x[r] W for R rows at once: every broadcast weight quad feeds 4*R FFMA
+template <int K, int R>
+__device__ __forceinline__ void dense20_rows(const float* __restrict__ sW, const float* __restrict__ sb,
+                                             const float (&x)[R][K], float (&h)[R][HID]) {
+#pragma unroll
+    for (int q = 0; q < HID / 4; ++q) {
+        const float4 v = reinterpret_cast<const float4*>(sb)[q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { h[r][4 * q] = v.x; h[r][4 * q + 1] = v.y; h[r][4 * q + 2] = v.z; h[r][4 * q + 3] = v.w; }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float4* w = reinterpret_cast<const float4*>(sW + k * HID);
+#pragma unroll
+        for (int q = 0; q < HID / 4; ++q) {
+            const float4 v = w[q];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                h[r][4 * q + 0] = fmaf(x[r][k], v.x, h[r][4 * q + 0]);
+                h[r][4 * q + 1] = fmaf(x[r][k], v.y, h[r][4 * q + 1]);
+                h[r][4 * q + 2] = fmaf(x[r][k], v.z, h[r][4 * q + 2]);
+                h[r][4 * q + 3] = fmaf(x[r][k], v.w, h[r][4 * q + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < HID; ++j) h[r][j] = lrelu(h[r][j]);
+}
+
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
+template <int NA, int DIN, int NOUT, int GRAD_WARPS>
+__device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad_job& job, float* smem) {
+    using L = TileLayout<DIN, NOUT>;
+    constexpr int NP = param_count(DIN, NOUT);
+    constexpr int R = 2;
+    rcmarl_rows Rw = P.rows;
+    if (job.time_idx) Rw.time_idx = job.time_idx;
+    float* sw = smem;
+    float* tiles = smem + round4(NP);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wt = tiles + warp * (L::ROWS * L::RS);
+
+    stage_weights(sw, job.w, NP);
+    __syncthreads();
+
+    // phase-2 assignment of this lane: tile `tile`, row group `grp`
+    const bool busy = lane < L::NG * L::NT;
+    const int tile = busy ? lane % L::NT : 0;
+    const int grp = busy ? lane / L::NT : 0;
+    int aoff, doff;
+    L::tile_offsets(tile, aoff, doff);
+    float acc[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+    float g3[L::L3T ? 1 : HID + 1];       // scalar nets: output-layer gradient per lane [W3(20) | b3]
+#pragma unroll
+    for (int j = 0; j < (L::L3T ? 1 : HID + 1); ++j) g3[j] = 0.f;
+    float loss = 0.f;
+
+    const int64_t nchunks = (Rw.n_rows + L::ROWS - 1) / L::ROWS;
+    for (int64_t c = (int64_t)blockIdx.y * GRAD_WARPS + warp; c < nchunks; c += (int64_t)gridDim.y * GRAD_WARPS) {
+        // ---------------- phase 1: two rows per lane (lane, lane + 32 of the chunk) ----------------
+        {
+            bool live[R];
+            int64_t row[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t m = c * L::ROWS + lane + 32 * r;
+                live[r] = m < Rw.n_rows;
+                row[r] = row_of(Rw, live[r] ? m : 0);      // dead rows read row 0 and contribute zeros
+            }
+            float h1[R][HID], h2[R][HID];
+            {
+                float x[R][DIN];
+#pragma unroll
+                for (int r = 0; r < R; ++r) load_x<NA, DIN>(Rw, job.kind, row[r], x[r]);
+                dense20_rows<DIN, R>(sw, sw + off_b1(DIN), x, h1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float* a1 = wt + (lane + 32 * r) * L::RS + L::OA1;
+#pragma unroll
+                    for (int q = 0; q < L::LA1 / 4; ++q) {
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = 4 * q + u;
+                            v[u] = k < DIN ? x[r][k < DIN ? k : 0] : (k == DIN ? 1.f : 0.f);
+                        }
+                        st4(a1 + 4 * q, v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+            dense20_rows<HID, R>(sw + off_W2(DIN), sw + off_b2(DIN), h1, h2);
+            float d2[R][HID];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float* rowp = wt + (lane + 32 * r) * L::RS;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) st4(rowp + L::OA2 + 4 * q, h1[r][4 * q], h1[r][4 * q + 1], h1[r][4 * q + 2], h1[r][4 * q + 3]);
+                st4(rowp + L::OA2 + 20, 1.f, 0.f, 0.f, 0.f);
+                const float tgt = live[r] ? __ldg(job.target + row[r] * job.target_stride) : 0.f;
+                const float* W3 = sw + off_W3(DIN);
+                if constexpr (NOUT == 1) {
+                    // Keras MSE (Appendix A.2): dLoss/dout = 2 (out - y) / B; the 2/B is applied by the caller
+                    const float e = live[r] ? head1<DIN>(sw, h2[r]) - tgt : 0.f;
+                    loss = fmaf(e, e, loss);
+#pragma unroll
+                    for (int j = 0; j < HID; ++j) {
+                        g3[j] = fmaf(h2[r][j], e, g3[j]);
+                        d2[r][j] = W3[j] * e * lrelu_grad_from_out(h2[r][j]);
+                    }
+                    g3[HID] += e;
+                } else {
+                    // weighted sparse categorical cross-entropy on the logits (Appendix A.5)
+                    float p[NACT], mx, lse, g[NACT];
+                    head5<DIN>(sw, h2[r], p);
+                    const int a = (int)__ldg(Rw.sa + row[r] * (3 * NA) + 3 * job.action_agent + 2);
+                    float la = 0.f;
+#pragma unroll
+                    for (int o = 0; o < NACT; ++o) la = (o == a) ? p[o] : la;
+                    softmax5(p, mx, lse);
+                    loss = fmaf(tgt, (mx + lse) - la, loss);
+#pragma unroll
+                    for (int o = 0; o < NACT; ++o) g[o] = (p[o] - (o == a ? 1.f : 0.f)) * tgt;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) st4(rowp + L::OA3 + 4 * q, h2[r][4 * q], h2[r][4 * q + 1], h2[r][4 * q + 2], h2[r][4 * q + 3]);
+                    st4(rowp + L::OA3 + 20, 1.f, 0.f, 0.f, 0.f);
+                    st4(rowp + L::OD3, g[0], g[1], g[2], g[3]);
+                    st4(rowp + L::OD3 + 4, g[4], 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < HID; ++j) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int o = 0; o < NACT; ++o) s = fmaf(W3[j * NACT + o], g[o], s);
+                        d2[r][j] = s * lrelu_grad_from_out(h2[r][j]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) st4(rowp + L::OD2 + 4 * q, d2[r][4 * q], d2[r][4 * q + 1], d2[r][4 * q + 2], d2[r][4 * q + 3]);
+                st4(rowp + L::OD2 + 20, 0.f, 0.f, 0.f, 0.f);
+            }
+            // delta1[i] = (W2[i][:] . delta2) * lrelu'(z1[i]) for both rows; each W2 quad feeds 8 FFMA
+            const float* W2 = sw + off_W2(DIN);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                float d1[R][4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int i = 4 * q + ii;
+                    const float4* w = reinterpret_cast<const float4*>(W2 + i * HID);
+                    float s[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) s[r] = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < 5; ++qq) {
+                        const float4 v = w[qq];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            s[r] = fmaf(v.x, d2[r][4 * qq + 0], s[r]);
+                            s[r] = fmaf(v.y, d2[r][4 * qq + 1], s[r]);
+                            s[r] = fmaf(v.z, d2[r][4 * qq + 2], s[r]);
+                            s[r] = fmaf(v.w, d2[r][4 * qq + 3], s[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) d1[r][ii] = s[r] * lrelu_grad_from_out(h1[r][i]);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    st4(wt + (lane + 32 * r) * L::RS + L::OD1 + 4 * q, d1[r][0], d1[r][1], d1[r][2], d1[r][3]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) st4(wt + (lane + 32 * r) * L::RS + L::OD1 + 20, 0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        // ---------------- phase 2: 8x8 register tile per lane, NG rows per step ----------------
+#pragma unroll 2
+        for (int it = 0; it < L::ROWS / L::NG; ++it) {
+            const float* rp = wt + (it * L::NG + grp) * L::RS;
+            const float4 a0 = *reinterpret_cast<const float4*>(rp + aoff);
+            const float4 a1 = *reinterpret_cast<const float4*>(rp + aoff + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(rp + doff);
+            const float4 d1 = *reinterpret_cast<const float4*>(rp + doff + 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[ii * 8 + jj] = fmaf(a[ii], d[jj], acc[ii * 8 + jj]);
+        }
+        __syncwarp();
+    }
+
+    // ---------------- CTA reduction (fixed order => bitwise reproducible) ----------------
+    __syncthreads();
+    float* red = tiles;                               // [GRAD_WARPS][32][64]
+    {
+        float4* dst = reinterpret_cast<float4*>(red + (warp * 32 + lane) * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+    float* red3 = red + GRAD_WARPS * 32 * 64;         // [GRAD_WARPS][HID + 2]: lane-private layer-3 sums + loss
+    loss = warp_sum(loss);
+    if (lane == 0) red3[warp * (HID + 2) + HID + 1] = loss;
+    if constexpr (!L::L3T) {
+#pragma unroll
+        for (int j = 0; j <= HID; ++j) {
+            const float s = warp_sum(g3[j]);
+            if (lane == 0) red3[warp * (HID + 2) + j] = s;
+        }
+    }
+    __syncthreads();
+    float* out = P.partial + ((int64_t)blockIdx.y * P.n_jobs + blockIdx.x) * P.stride;
+    for (int q = threadIdx.x; q < L::NT * 64; q += blockDim.x) {
+        const int t = q >> 6, e = q & 63;
+        const int idx = L::tile_param(t, e >> 3, e & 7);
+        if (idx >= 0) {
+            float s = 0.f;
+            for (int w = 0; w < GRAD_WARPS; ++w)
+#pragma unroll
+                for (int g = 0; g < L::NG; ++g) s += red[(w * 32 + g * L::NT + t) * 64 + e];
+            out[idx] = s;
+        }
+    }
+    if constexpr (!L::L3T) {
+        if (threadIdx.x <= HID) {
+            float s = 0.f;
+            for (int w = 0; w < GRAD_WARPS; ++w) s += red3[w * (HID + 2) + threadIdx.x];
+            out[(threadIdx.x < HID ? off_W3(DIN) : off_b3(DIN, 1) - HID) + threadIdx.x] = s;
+        }
+    }
+    if (threadIdx.x == 32) {
+        float s = 0.f;
+        for (int w = 0; w < GRAD_WARPS; ++w) s += red3[w * (HID + 2) + HID + 1];
+        out[NP] = s;
+    }
+}
+
+template <int NA, int LOSS>
+__global__ void __launch_bounds__(32 * grad_warps<NA, LOSS>(), 1) grad_kernel(const __grid_constant__ GradParams P) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NW = grad_warps<NA, LOSS>();
+    const rcmarl_grad_job& job = P.jobs[blockIdx.x];
+    if (LOSS == RCMARL_LOSS_CE) {
+        grad_body<NA, 2 * NA, NACT, NW>(P, job, smem);
+    } else if (job.kind == RCMARL_IN_SA) {
+        grad_body<NA, 3 * NA, 1, NW>(P, job, smem);
+    } else {
+        grad_body<NA, 2 * NA, 1, NW>(P, job, smem);
+    }
+}
+
+template <int DIN, int NOUT, int NW>
+constexpr int grad_smem_floats() {
+    using L = TileLayout<DIN, NOUT>;
+    const int tiles = NW * L::ROWS * L::RS;
+    const int red = NW * 32 * 64 + NW * (HID + 2);
+    return round4(param_count(DIN, NOUT)) + (tiles > red ? tiles : red) + 16;
+}
+
+}  // namespace rcmarl

@@ -13,6 +13,7 @@
 // Reference semantics: agents/resilient_CAC_agents.py, agents/adversarial_CAC_agents.py,
 // training/train_agents.py:86-163 (cited per entry point in include/rcmarl.h).
 #include "common.cuh"
+#include "grad_kernel.cuh"
 
 namespace rcmarl {
 
@@ -95,265 +96,6 @@ __global__ void __launch_bounds__(256) values_kernel(const __grid_constant__ Val
             }
         }
     }
-}
-
-// ============================================================================================
-// grad
-// ============================================================================================
-template <int DIN, int NOUT>
-struct RowLayout {
-    static constexpr int LA1 = round4(DIN + 1);
-    static constexpr int OA1 = 0;
-    static constexpr int OA2 = LA1;
-    static constexpr int OA3 = LA1 + 24;
-    static constexpr int OD1 = LA1 + 48;
-    static constexpr int OD2 = LA1 + 68;
-    static constexpr int OD3 = LA1 + 88;
-    static constexpr int LD3 = round4(NOUT);
-    static constexpr int RAW = LA1 + 88 + LD3;
-    // row stride with an odd number of 16-byte units: conflict-free float4 stores per quarter-warp
-    static constexpr int RS = ((RAW / 4) % 2 == 0) ? RAW + 4 : RAW;
-    static constexpr int NI1 = LA1 / 4;
-    static constexpr int JB3 = LD3 / 4;
-    static constexpr int NB1 = NI1 * 5;
-    static constexpr int NB2 = 30;
-    static constexpr int NB3 = 6 * JB3;
-    static constexpr int NBLK = NB1 + NB2 + NB3;
-    static constexpr int NPASS = (NBLK + 31) / 32;
-
-    __device__ static __forceinline__ void block_offsets(int b, int& aoff, int& doff) {
-        if (b < NB1) {
-            aoff = OA1 + 4 * (b / 5); doff = OD1 + 4 * (b % 5);
-        } else if (b < NB1 + NB2) {
-            b -= NB1; aoff = OA2 + 4 * (b / 5); doff = OD2 + 4 * (b % 5);
-        } else if (b < NBLK) {
-            b -= NB1 + NB2; aoff = OA3 + 4 * (b / JB3); doff = OD3 + 4 * (b % JB3);
-        } else {
-            aoff = 0; doff = 0;
-        }
-    }
-    // packed-parameter index of element (ii, jj) of block b, -1 for padding
-    __device__ static __forceinline__ int block_param(int b, int ii, int jj) {
-        if (b < NB1) {
-            int i = 4 * (b / 5) + ii, j = 4 * (b % 5) + jj;
-            return i < DIN ? i * HID + j : (i == DIN ? off_b1(DIN) + j : -1);
-        } else if (b < NB1 + NB2) {
-            b -= NB1;
-            int i = 4 * (b / 5) + ii, j = 4 * (b % 5) + jj;
-            return i < HID ? off_W2(DIN) + i * HID + j : (i == HID ? off_b2(DIN) + j : -1);
-        } else if (b < NBLK) {
-            b -= NB1 + NB2;
-            int i = 4 * (b / JB3) + ii, o = 4 * (b % JB3) + jj;
-            if (o >= NOUT) return -1;
-            return i < HID ? off_W3(DIN) + i * NOUT + o : (i == HID ? off_b3(DIN, NOUT) + o : -1);
-        }
-        return -1;
-    }
-};
-
-constexpr int GRAD_THREADS = 224;  // 7 warps: two CTAs (2 x ~101 KB of shared memory) per SM at n_agents = 5
-
-struct GradParams {
-    rcmarl_rows rows;
-    rcmarl_grad_job jobs[RCMARL_MAX_JOBS];
-    float* partial;   // [gridDim.y][n_jobs][stride]
-    int32_t n_jobs;
-    int32_t stride;
-};
-
-template <int NA, int DIN, int NOUT>
-__device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad_job& job, float* smem) {
-    using L = RowLayout<DIN, NOUT>;
-    constexpr int NP = param_count(DIN, NOUT);
-    rcmarl_rows R = P.rows;
-    if (job.time_idx) R.time_idx = job.time_idx;
-    float* sw = smem;
-    float* tiles = smem + round4(NP);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    float* wt = tiles + warp * (32 * L::RS);
-    float* myrow = wt + lane * L::RS;
-
-    stage_weights(sw, job.w, NP);
-    __syncthreads();
-
-    int aoff[L::NPASS], doff[L::NPASS];
-    float acc[L::NPASS][16];
-#pragma unroll
-    for (int p = 0; p < L::NPASS; ++p) {
-        L::block_offsets(p * 32 + lane, aoff[p], doff[p]);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[p][e] = 0.f;
-    }
-    float loss = 0.f;
-
-    const int64_t nchunks = (R.n_rows + 31) >> 5;
-    for (int64_t c = (int64_t)blockIdx.y * nwarps + warp; c < nchunks; c += (int64_t)gridDim.y * nwarps) {
-        const int64_t m = c * 32 + lane;
-        // ---------------- phase 1: one row per lane ----------------
-        if (m < R.n_rows) {
-            const int64_t row = row_of(R, m);
-            float h1[HID], h2[HID];
-            {
-                float x[DIN];
-                load_x<NA, DIN>(R, job.kind, row, x);
-                dense20<DIN>(sw, sw + off_b1(DIN), x, h1);
-                float4* a1 = reinterpret_cast<float4*>(myrow + L::OA1);
-#pragma unroll
-                for (int q = 0; q < L::NI1; ++q) {
-                    float4 v;
-                    v.x = (4 * q + 0 < DIN) ? x[(4 * q + 0 < DIN) ? 4 * q + 0 : 0] : (4 * q + 0 == DIN ? 1.f : 0.f);
-                    v.y = (4 * q + 1 < DIN) ? x[(4 * q + 1 < DIN) ? 4 * q + 1 : 0] : (4 * q + 1 == DIN ? 1.f : 0.f);
-                    v.z = (4 * q + 2 < DIN) ? x[(4 * q + 2 < DIN) ? 4 * q + 2 : 0] : (4 * q + 2 == DIN ? 1.f : 0.f);
-                    v.w = (4 * q + 3 < DIN) ? x[(4 * q + 3 < DIN) ? 4 * q + 3 : 0] : (4 * q + 3 == DIN ? 1.f : 0.f);
-                    a1[q] = v;
-                }
-            }
-            dense20<HID>(sw + off_W2(DIN), sw + off_b2(DIN), h1, h2);
-            float4* a2 = reinterpret_cast<float4*>(myrow + L::OA2);
-            float4* a3 = reinterpret_cast<float4*>(myrow + L::OA3);
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                a2[q] = make_float4(h1[4 * q], h1[4 * q + 1], h1[4 * q + 2], h1[4 * q + 3]);
-                a3[q] = make_float4(h2[4 * q], h2[4 * q + 1], h2[4 * q + 2], h2[4 * q + 3]);
-            }
-            a2[5] = make_float4(1.f, 0.f, 0.f, 0.f);
-            a3[5] = make_float4(1.f, 0.f, 0.f, 0.f);
-
-            float d2[HID];
-            const float tgt = __ldg(job.target + row * job.target_stride);
-            if constexpr (NOUT == 1) {
-                // Keras MSE (Appendix A.2): dLoss/dout = 2 (out - y) / B; the 2/B is applied later
-                const float e = head1<DIN>(sw, h2) - tgt;
-                loss = fmaf(e, e, loss);
-                *reinterpret_cast<float4*>(myrow + L::OD3) = make_float4(e, 0.f, 0.f, 0.f);
-                const float* W3 = sw + off_W3(DIN);
-#pragma unroll
-                for (int j = 0; j < HID; ++j) d2[j] = W3[j] * e * lrelu_grad_from_out(h2[j]);
-            } else {
-                // weighted sparse categorical cross-entropy on the logits (Appendix A.5)
-                float p[NACT], mx, lse, g[NACT];
-                head5<DIN>(sw, h2, p);
-                const int a = (int)__ldg(R.sa + row * (3 * NA) + 3 * job.action_agent + 2);
-                float la = 0.f;
-#pragma unroll
-                for (int o = 0; o < NACT; ++o) la = (o == a) ? p[o] : la;
-                softmax5(p, mx, lse);
-                loss = fmaf(tgt, (mx + lse) - la, loss);
-#pragma unroll
-                for (int o = 0; o < NACT; ++o) g[o] = (p[o] - (o == a ? 1.f : 0.f)) * tgt;
-                float4* d3 = reinterpret_cast<float4*>(myrow + L::OD3);
-                d3[0] = make_float4(g[0], g[1], g[2], g[3]);
-                d3[1] = make_float4(g[4], 0.f, 0.f, 0.f);
-                const float* W3 = sw + off_W3(DIN);
-#pragma unroll
-                for (int j = 0; j < HID; ++j) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int o = 0; o < NACT; ++o) s = fmaf(W3[j * NACT + o], g[o], s);
-                    d2[j] = s * lrelu_grad_from_out(h2[j]);
-                }
-            }
-            float4* dd2 = reinterpret_cast<float4*>(myrow + L::OD2);
-#pragma unroll
-            for (int q = 0; q < 5; ++q) dd2[q] = make_float4(d2[4 * q], d2[4 * q + 1], d2[4 * q + 2], d2[4 * q + 3]);
-            // d1[i] = (W2[i][:] . d2) * lrelu'(z1[i])
-            float4* dd1 = reinterpret_cast<float4*>(myrow + L::OD1);
-            const float* W2 = sw + off_W2(DIN);
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                float d1[4];
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int i = 4 * q + ii;
-                    const float4* w = reinterpret_cast<const float4*>(W2 + i * HID);
-                    float s = 0.f;
-#pragma unroll
-                    for (int qq = 0; qq < 5; ++qq) {
-                        float4 v = w[qq];
-                        s = fmaf(v.x, d2[4 * qq + 0], s);
-                        s = fmaf(v.y, d2[4 * qq + 1], s);
-                        s = fmaf(v.z, d2[4 * qq + 2], s);
-                        s = fmaf(v.w, d2[4 * qq + 3], s);
-                    }
-                    d1[ii] = s * lrelu_grad_from_out(h1[i]);
-                }
-                dd1[q] = make_float4(d1[0], d1[1], d1[2], d1[3]);
-            }
-        } else {
-            float4* z = reinterpret_cast<float4*>(myrow);
-#pragma unroll
-            for (int q = 0; q < L::RS / 4; ++q) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-        // ---------------- phase 2: lane-owned 4x4 blocks of the outer products ----------------
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            const float* rp = wt + r * L::RS;
-#pragma unroll
-            for (int p = 0; p < L::NPASS; ++p) {
-                const float4 a = *reinterpret_cast<const float4*>(rp + aoff[p]);
-                const float4 d = *reinterpret_cast<const float4*>(rp + doff[p]);
-                acc[p][0] = fmaf(a.x, d.x, acc[p][0]);   acc[p][1] = fmaf(a.x, d.y, acc[p][1]);
-                acc[p][2] = fmaf(a.x, d.z, acc[p][2]);   acc[p][3] = fmaf(a.x, d.w, acc[p][3]);
-                acc[p][4] = fmaf(a.y, d.x, acc[p][4]);   acc[p][5] = fmaf(a.y, d.y, acc[p][5]);
-                acc[p][6] = fmaf(a.y, d.z, acc[p][6]);   acc[p][7] = fmaf(a.y, d.w, acc[p][7]);
-                acc[p][8] = fmaf(a.z, d.x, acc[p][8]);   acc[p][9] = fmaf(a.z, d.y, acc[p][9]);
-                acc[p][10] = fmaf(a.z, d.z, acc[p][10]); acc[p][11] = fmaf(a.z, d.w, acc[p][11]);
-                acc[p][12] = fmaf(a.w, d.x, acc[p][12]); acc[p][13] = fmaf(a.w, d.y, acc[p][13]);
-                acc[p][14] = fmaf(a.w, d.z, acc[p][14]); acc[p][15] = fmaf(a.w, d.w, acc[p][15]);
-            }
-        }
-        __syncwarp();
-    }
-
-    // ---------------- CTA reduction (fixed order => bitwise reproducible) ----------------
-    __syncthreads();
-    float* red = tiles;  // [nwarps][NPASS*512]
-#pragma unroll
-    for (int p = 0; p < L::NPASS; ++p) {
-        float4* dst = reinterpret_cast<float4*>(red + (warp * L::NPASS + p) * 512 + lane * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            dst[q] = make_float4(acc[p][4 * q], acc[p][4 * q + 1], acc[p][4 * q + 2], acc[p][4 * q + 3]);
-    }
-    loss = warp_sum(loss);
-    float* red_loss = red + nwarps * L::NPASS * 512;
-    if (lane == 0) red_loss[warp] = loss;
-    __syncthreads();
-    float* out = P.partial + ((int64_t)blockIdx.y * P.n_jobs + blockIdx.x) * P.stride;
-    for (int q = threadIdx.x; q < L::NPASS * 512; q += blockDim.x) {
-        const int p = q >> 9, ln = (q >> 4) & 31, e = q & 15;
-        const int idx = L::block_param(p * 32 + ln, e >> 2, e & 3);
-        if (idx >= 0) {
-            float s = 0.f;
-            for (int w = 0; w < nwarps; ++w) s += red[(w * L::NPASS + p) * 512 + ln * 16 + e];
-            out[idx] = s;
-        }
-    }
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < nwarps; ++w) s += red_loss[w];
-        out[NP] = s;
-    }
-}
-
-template <int NA, int LOSS>
-__global__ void __launch_bounds__(GRAD_THREADS, (NA <= 5 ? 2 : 1))
-grad_kernel(const __grid_constant__ GradParams P) {
-    extern __shared__ __align__(16) float smem[];
-    const rcmarl_grad_job& job = P.jobs[blockIdx.x];
-    if (LOSS == RCMARL_LOSS_CE) {
-        grad_body<NA, 2 * NA, NACT>(P, job, smem);
-    } else if (job.kind == RCMARL_IN_SA) {
-        grad_body<NA, 3 * NA, 1>(P, job, smem);
-    } else {
-        grad_body<NA, 2 * NA, 1>(P, job, smem);
-    }
-}
-
-template <int DIN, int NOUT>
-constexpr int grad_smem_floats() {
-    return round4(param_count(DIN, NOUT)) + (GRAD_THREADS / 32) * 32 * RowLayout<DIN, NOUT>::RS + 64;
 }
 
 // sums[j][i] = sum_y partial[y][j][i], y ascending (deterministic)
@@ -558,18 +300,25 @@ static int launch_values(const ValuesParams& P, int n_jobs, cudaStream_t st) {
 
 template <int NA>
 static int launch_grad(GradParams& P, int loss_mode, int gy, cudaStream_t st) {
-    constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<3 * NA, 1>() > grad_smem_floats<2 * NA, 1>()
-                                                     ? grad_smem_floats<3 * NA, 1>() : grad_smem_floats<2 * NA, 1>());
-    constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<2 * NA, NACT>();
+    constexpr int NWM = grad_warps<NA, RCMARL_LOSS_MSE>(), NWC = grad_warps<NA, RCMARL_LOSS_CE>();
+    constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<3 * NA, 1, NWM>() > grad_smem_floats<2 * NA, 1, NWM>()
+                                                     ? grad_smem_floats<3 * NA, 1, NWM>() : grad_smem_floats<2 * NA, 1, NWM>());
+    constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<2 * NA, NACT, NWC>();
     if (loss_mode == RCMARL_LOSS_CE) {
         if (set_smem(grad_kernel<NA, RCMARL_LOSS_CE>, smem_ce)) return RCMARL_ERR_CUDA;
-        grad_kernel<NA, RCMARL_LOSS_CE><<<dim3(P.n_jobs, gy), GRAD_THREADS, smem_ce, st>>>(P);
+        grad_kernel<NA, RCMARL_LOSS_CE><<<dim3(P.n_jobs, gy), 32 * NWC, smem_ce, st>>>(P);
     } else {
         if (set_smem(grad_kernel<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
-        grad_kernel<NA, RCMARL_LOSS_MSE><<<dim3(P.n_jobs, gy), GRAD_THREADS, smem_mse, st>>>(P);
+        grad_kernel<NA, RCMARL_LOSS_MSE><<<dim3(P.n_jobs, gy), 32 * NWM, smem_mse, st>>>(P);
     }
     RC_CUDA(cudaGetLastError());
     return 0;
+}
+
+// chunks (64 rows) one CTA of this configuration consumes per sweep
+template <int NA>
+static int grad_chunks_per_cta(int loss_mode) {
+    return loss_mode == RCMARL_LOSS_CE ? grad_warps<NA, RCMARL_LOSS_CE>() : grad_warps<NA, RCMARL_LOSS_MSE>();
 }
 
 template <int NA>
@@ -641,8 +390,9 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
         Q.n[j] = n + 1;
         if (n + 1 > maxn) maxn = n + 1;
     }
-    const int64_t nchunks = (rows->n_rows + 31) / 32;
-    const int gy = grid_y_for((nchunks + GRAD_THREADS / 32 - 1) / (GRAD_THREADS / 32), n_jobs, NA <= 5 ? 2 : 1);
+    const int64_t nchunks = (rows->n_rows + 63) / 64;
+    const int cpc = NA == 5 ? grad_chunks_per_cta<5>(loss_mode) : grad_chunks_per_cta<16>(loss_mode);
+    const int gy = grid_y_for((nchunks + cpc - 1) / cpc, n_jobs, 1);
     if ((int64_t)gy * n_jobs * maxn * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
     P.partial = (float*)ws;
     P.n_jobs = n_jobs;
@@ -670,7 +420,7 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
     bool any_sums = false;
     for (int j = 0; j < n_jobs; ++j) {
         const rcmarl_team_job& q = jobs[j];
-        if (!q.w || q.kind < 0 || q.kind > 1) return RCMARL_ERR_ARG;
+        if (!q.w || q.kind < 0 || q.kind > 2) return RCMARL_ERR_ARG;
         if (!q.agg_in) {
             if (!q.msgs || q.n_in < 1 || q.n_in > RCMARL_MAX_NEIGHBOURS || q.H < 0 || q.H >= q.n_in) return RCMARL_ERR_ARG;
         }

@@ -1,0 +1,122 @@
+"""GPU parity of the batched training engine (rcmarl.trainer.Trainer) against
+ (a) the golden run of the reference's own train_RPBCAC executed verbatim on the facade
+     (tests/golden/ref_train_run.npz: 2 update rounds, 4 cooperative + 1 malicious, H=1), and
+ (b) the CPU oracle on a batched (n_envs > 1) configuration incl. Greedy / Faulty agents.
+Tolerance: weights after full update rounds rtol 1e-3 / atol 5e-5 (hundreds of chained fp32 SGD steps;
+single steps are held to 1e-4 in test_kernels_gpu.py)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from golden_util import load, agent_weights, pretrained    # noqa: E402
+from oracle import rpbcac_oracle as O                        # noqa: E402
+
+IN_NODES = [[0, 1, 2, 3], [1, 2, 3, 4], [2, 3, 4, 0], [3, 4, 0, 1], [4, 0, 1, 2]]
+
+
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def close_w(got, want, rtol=1e-3, atol=5e-5):
+    for n in range(len(want)):
+        for k in range(6):
+            np.testing.assert_allclose(np.asarray(got[n][k], np.float64), np.asarray(want[n][k], np.float64),
+                                       rtol=rtol, atol=atol, err_msg=f"net {n} array {k}")
+
+
+def test_two_update_rounds_match_reference_train_run():
+    need_gpu()
+    from rcmarl.trainer import Trainer
+    z = load("ref_train_run.npz")
+    w, desired, labels = pretrained()
+    perms = [z[f"perm{j}"] for j in range(int(z["n_perms"]))]
+    it = iter(perms)
+
+    def perm_source(T):
+        p = next(it)
+        assert len(p) == T
+        return p
+    tr = Trainer(labels=labels, in_nodes=IN_NODES, weights=w, desired=desired, n_envs=1, gamma=0.9, H=1, fast_lr=0.01,
+                 slow_lr=0.002, max_ep_len=10, n_ep_fixed=25, n_epochs=2, buffer_size=100000, capacity_times=600,
+                 perm_source=perm_source)
+    for rnd in (0, 1):
+        sl = slice(250 * rnd, 250 * (rnd + 1))
+        tr.load_rows(z["s"][sl], z["ns"][sl], z["a"][sl], z["r"][sl])
+        tr.update_round()
+    assert next(it, None) is None
+    final = agent_weights(z, "final")
+    for i in range(5):
+        close_w(tr.get_weights(i), final[i])
+
+
+@pytest.mark.parametrize("labels,common,H", [
+    (['Cooperative'] * 5, False, 0),
+    (['Cooperative', 'Cooperative', 'Cooperative', 'Greedy', 'Faulty'], True, 1),
+    (['Cooperative', 'Cooperative', 'Cooperative', 'Cooperative', 'Malicious'], False, 1)])
+def test_batched_update_round_matches_oracle(labels, common, H):
+    need_gpu()
+    from rcmarl.trainer import Trainer
+    rs = np.random.RandomState(3)
+    N, T1, gamma = 6, 48, 0.9
+    w, desired, _ = pretrained()
+
+    def make_oracle():
+        ags = []
+        for i, l in enumerate(labels):
+            a, c, t = w[i][0], w[i][1], w[i][2]
+            if l == 'Cooperative':
+                ags.append(O.RPBCACOracleAgent(a, c, t, 0.002, 0.01, gamma, H=H, dtype=np.float64))
+            elif l == 'Malicious':
+                ags.append(O.MaliciousOracleAgent(a, c, t, 0.002, 0.01, gamma, critic_local_w=w[i][3], dtype=np.float64))
+            elif l == 'Greedy':
+                ags.append(O.GreedyOracleAgent(a, c, t, 0.002, 0.01, gamma, dtype=np.float64))
+            else:
+                ags.append(O.FaultyOracleAgent(a, c, t, 0.002, gamma, dtype=np.float64))
+        return ags
+    agents = make_oracle()
+    rs_perm = np.random.RandomState(4)
+    used = []
+
+    def perm_rec(T):
+        p = rs_perm.permutation(T)
+        used.append(p)
+        return p
+    it = None
+
+    def perm_replay(T):
+        p = next(it)
+        assert len(p) == T
+        return p
+    tr = Trainer(labels=labels, in_nodes=IN_NODES, weights=w, desired=desired, n_envs=N, gamma=gamma, H=H, fast_lr=0.01,
+                 slow_lr=0.002, max_ep_len=8, n_ep_fixed=6, n_epochs=2, buffer_size=64, common_reward=common,
+                 perm_source=perm_replay)
+    S = NS = A = R = None
+    for rnd in range(2):
+        B = T1 * N
+        pos = rs.randint(0, 5, size=(B, 5, 2))
+        npos = np.clip(pos + rs.randint(-1, 2, size=pos.shape), 0, 4)
+        s = ((pos - 2.0) / np.std(np.arange(5))).astype(np.float32)
+        ns = ((npos - 2.0) / np.std(np.arange(5))).astype(np.float32)
+        a = rs.randint(0, 5, size=(B, 5, 1)).astype(np.float32)
+        r = (-rs.randint(0, 9, size=(B, 5, 1)) / 5.0).astype(np.float32)
+        S, NS, A, R = (s, ns, a, r) if S is None else tuple(np.concatenate([x, y]) for x, y in ((S, s), (NS, ns), (A, a), (R, r)))
+        used.clear()
+        want_loss = O.update_round(agents, labels, IN_NODES, S, NS, A, R, n_envs=N, n_epochs=2, n_actor_steps=48,
+                                   common_reward=common, perm_source=perm_rec)
+        it = iter(list(used))
+        tr.load_rows(s, ns, a, r)
+        got_loss = tr.update_round()
+        assert next(it, None) is None
+        for k in ("critic_loss", "TR_loss", "actor_loss"):
+            np.testing.assert_allclose(got_loss[k], want_loss[k], rtol=2e-3, atol=2e-5, err_msg=k)
+        # oracle-side trim (train_agents.py:158-163): newest 64 time rows
+        keep = 64 * N
+        S, NS, A, R = S[-keep:], NS[-keep:], A[-keep:], R[-keep:]
+        assert tr.t_filled == min(64, T1 * (rnd + 1))
+        np.testing.assert_array_equal(tr.ns[:tr.t_filled * N].cpu().numpy().reshape(-1, 5, 2), NS)
+    for i in range(5):
+        close_w(tr.get_weights(i), agents[i].get_parameters())
