@@ -97,35 +97,60 @@ struct GradParams {
     int32_t stride;
 };
 
-// z[r][:] = b + x[r] W for R rows at once: every broadcast weight quad feeds 4*R FFMA
+// Blackwell packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): two IEEE fp32 FMAs per issue slot.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// z[r][:] = b + x[r] W for R rows at once: every broadcast weight quad (uniform LDS.128) feeds 2*R FFMA2;
+// outputs are packed as pairs of adjacent hidden units.
 template <int K, int R>
 __device__ __forceinline__ void dense20_rows(const float* __restrict__ sW, const float* __restrict__ sb,
                                              const float (&x)[R][K], float (&h)[R][HID]) {
+    f2 hp[R][HID / 2];
 #pragma unroll
     for (int q = 0; q < HID / 4; ++q) {
         const float4 v = reinterpret_cast<const float4*>(sb)[q];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { h[r][4 * q] = v.x; h[r][4 * q + 1] = v.y; h[r][4 * q + 2] = v.z; h[r][4 * q + 3] = v.w; }
+        for (int r = 0; r < R; ++r) { hp[r][2 * q] = pack2(v.x, v.y); hp[r][2 * q + 1] = pack2(v.z, v.w); }
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float4* w = reinterpret_cast<const float4*>(sW + k * HID);
+        f2 xk[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xk[r] = pack2(x[r][k], x[r][k]);
 #pragma unroll
         for (int q = 0; q < HID / 4; ++q) {
             const float4 v = w[q];
+            const f2 w0 = pack2(v.x, v.y), w1 = pack2(v.z, v.w);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                h[r][4 * q + 0] = fmaf(x[r][k], v.x, h[r][4 * q + 0]);
-                h[r][4 * q + 1] = fmaf(x[r][k], v.y, h[r][4 * q + 1]);
-                h[r][4 * q + 2] = fmaf(x[r][k], v.z, h[r][4 * q + 2]);
-                h[r][4 * q + 3] = fmaf(x[r][k], v.w, h[r][4 * q + 3]);
+                hp[r][2 * q] = fma2(xk[r], w0, hp[r][2 * q]);
+                hp[r][2 * q + 1] = fma2(xk[r], w1, hp[r][2 * q + 1]);
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int j = 0; j < HID; ++j) h[r][j] = lrelu(h[r][j]);
+        for (int j = 0; j < HID / 2; ++j) {
+            float a, b;
+            unpack2(hp[r][j], a, b);
+            h[r][2 * j] = lrelu(a);
+            h[r][2 * j + 1] = lrelu(b);
+        }
 }
 
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
@@ -153,9 +178,9 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     const int grp = busy ? lane / L::NT : 0;
     int aoff, doff;
     L::tile_offsets(tile, aoff, doff);
-    float acc[64];
+    f2 acc[32];                            // 8x8 tile, packed as pairs over the delta index
 #pragma unroll
-    for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+    for (int e = 0; e < 32; ++e) acc[e] = pack2(0.f, 0.f);
     float g3[L::L3T ? 1 : HID + 1];       // scalar nets: output-layer gradient per lane [W3(20) | b3]
 #pragma unroll
     for (int j = 0; j < (L::L3T ? 1 : HID + 1); ++j) g3[j] = 0.f;
@@ -245,6 +270,11 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
             }
             // delta1[i] = (W2[i][:] . delta2) * lrelu'(z1[i]) for both rows; each W2 quad feeds 8 FFMA
             const float* W2 = sw + off_W2(DIN);
+            f2 d2p[R][HID / 2];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < HID / 2; ++j) d2p[r][j] = pack2(d2[r][2 * j], d2[r][2 * j + 1]);
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 float d1[R][4];
@@ -252,22 +282,25 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
                 for (int ii = 0; ii < 4; ++ii) {
                     const int i = 4 * q + ii;
                     const float4* w = reinterpret_cast<const float4*>(W2 + i * HID);
-                    float s[R];
+                    f2 s[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) s[r] = 0.f;
+                    for (int r = 0; r < R; ++r) s[r] = pack2(0.f, 0.f);
 #pragma unroll
                     for (int qq = 0; qq < 5; ++qq) {
                         const float4 v = w[qq];
+                        const f2 w0 = pack2(v.x, v.y), w1 = pack2(v.z, v.w);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            s[r] = fmaf(v.x, d2[r][4 * qq + 0], s[r]);
-                            s[r] = fmaf(v.y, d2[r][4 * qq + 1], s[r]);
-                            s[r] = fmaf(v.z, d2[r][4 * qq + 2], s[r]);
-                            s[r] = fmaf(v.w, d2[r][4 * qq + 3], s[r]);
+                            s[r] = fma2(w0, d2p[r][2 * qq], s[r]);
+                            s[r] = fma2(w1, d2p[r][2 * qq + 1], s[r]);
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < R; ++r) d1[r][ii] = s[r] * lrelu_grad_from_out(h1[r][i]);
+                    for (int r = 0; r < R; ++r) {
+                        float se, so;
+                        unpack2(s[r], se, so);
+                        d1[r][ii] = (se + so) * lrelu_grad_from_out(h1[r][i]);
+                    }
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r)
@@ -286,11 +319,13 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
             const float4 d0 = *reinterpret_cast<const float4*>(rp + doff);
             const float4 d1 = *reinterpret_cast<const float4*>(rp + doff + 4);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            const f2 d[4] = {pack2(d0.x, d0.y), pack2(d0.z, d0.w), pack2(d1.x, d1.y), pack2(d1.z, d1.w)};
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii)
+            for (int ii = 0; ii < 8; ++ii) {
+                const f2 aa = pack2(a[ii], a[ii]);
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) acc[ii * 8 + jj] = fmaf(a[ii], d[jj], acc[ii * 8 + jj]);
+                for (int jp = 0; jp < 4; ++jp) acc[ii * 4 + jp] = fma2(aa, d[jp], acc[ii * 4 + jp]);
+            }
         }
         __syncwarp();
     }
@@ -301,7 +336,12 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     {
         float4* dst = reinterpret_cast<float4*>(red + (warp * 32 + lane) * 64);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        for (int q = 0; q < 16; ++q) {
+            float4 v;
+            unpack2(acc[2 * q], v.x, v.y);
+            unpack2(acc[2 * q + 1], v.z, v.w);
+            dst[q] = v;
+        }
     }
     float* red3 = red + GRAD_WARPS * 32 * 64;         // [GRAD_WARPS][HID + 2]: lane-private layer-3 sums + loss
     loss = warp_sum(loss);

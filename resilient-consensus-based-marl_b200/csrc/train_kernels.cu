@@ -331,7 +331,9 @@ static int launch_team(const TeamParams& P, int gy, cudaStream_t st) {
 }
 
 static int grid_y_for(int64_t work_items, int n_jobs, int ctas_per_sm) {
-    int64_t cap = ((int64_t)sm_count_cached() * ctas_per_sm + n_jobs - 1) / n_jobs;
+    // one resident wave at most: gridDim.x * gridDim.y <= SMs * CTAs-per-SM (a partial second wave would
+    // double the kernel time of these persistent, equal-work CTAs)
+    int64_t cap = ((int64_t)sm_count_cached() * ctas_per_sm) / n_jobs;
     if (cap < 1) cap = 1;
     int64_t gy = work_items < cap ? work_items : cap;
     return (int)(gy < 1 ? 1 : gy);
