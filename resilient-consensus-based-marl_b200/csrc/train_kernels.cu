@@ -114,6 +114,27 @@ __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ Red
     P.sums[j][i] = s;
 }
 
+// fused: sums[j][i] = sum_y partial[y][j][i]; theta = theta - coef * sums (mini-batch SGD step, single GPU)
+struct ReduceSgdParams {
+    const float* partial;
+    rcmarl_sgd_job jobs[RCMARL_MAX_JOBS];
+    int32_t n_jobs, stride, gy;
+};
+__global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__ ReduceSgdParams P) {
+    const rcmarl_sgd_job& job = P.jobs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > job.n) return;
+    float s = 0.f;
+    for (int y = 0; y < P.gy; ++y) s += P.partial[((int64_t)y * P.n_jobs + blockIdx.y) * P.stride + i];
+    if (i < job.n) {
+        const float v = job.src[i];
+        job.dst[i] = i >= job.first ? v - job.coef * s : v;
+    } else if (job.loss_out) {
+        const float l = job.loss_coef * s;
+        *job.loss_out = job.loss_accumulate ? *job.loss_out + l : l;
+    }
+}
+
 // ============================================================================================
 // team: estimates + clipped mean + projection numerators
 // ============================================================================================
@@ -304,11 +325,18 @@ static int launch_grad(GradParams& P, int loss_mode, int gy, cudaStream_t st) {
     constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<3 * NA, 1, NWM>() > grad_smem_floats<2 * NA, 1, NWM>()
                                                      ? grad_smem_floats<3 * NA, 1, NWM>() : grad_smem_floats<2 * NA, 1, NWM>());
     constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<2 * NA, NACT, NWC>();
+    static bool attr_ce = false, attr_mse = false;     // opt-in to > 48 KB dynamic shared memory once per process
     if (loss_mode == RCMARL_LOSS_CE) {
-        if (set_smem(grad_kernel<NA, RCMARL_LOSS_CE>, smem_ce)) return RCMARL_ERR_CUDA;
+        if (!attr_ce) {
+            if (set_smem(grad_kernel<NA, RCMARL_LOSS_CE>, smem_ce)) return RCMARL_ERR_CUDA;
+            attr_ce = true;
+        }
         grad_kernel<NA, RCMARL_LOSS_CE><<<dim3(P.n_jobs, gy), 32 * NWC, smem_ce, st>>>(P);
     } else {
-        if (set_smem(grad_kernel<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
+        if (!attr_mse) {
+            if (set_smem(grad_kernel<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
+            attr_mse = true;
+        }
         grad_kernel<NA, RCMARL_LOSS_MSE><<<dim3(P.n_jobs, gy), 32 * NWM, smem_mse, st>>>(P);
     }
     RC_CUDA(cudaGetLastError());
@@ -408,6 +436,59 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
     Q.gy = gy;
     reduce_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
     RC_CUDA(cudaGetLastError());
+    return RCMARL_OK;
+}
+
+int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, const rcmarl_sgd_job* sjobs, int n_jobs,
+                         int epochs, int n_times, int mb_times, float lr, void* ws, int64_t ws_bytes, void* stream) {
+    if (!rows || !rows->sa || !rows->ns || !rows->r || rows->n_envs <= 0) return RCMARL_ERR_ARG;
+    if (rows->n_agents != 5 && rows->n_agents != 16) return RCMARL_ERR_ARG;
+    if (!gjobs || !sjobs || n_jobs < 1 || n_jobs > RCMARL_MAX_JOBS || !ws || epochs < 1 || n_times < 1 || mb_times < 1)
+        return RCMARL_ERR_ARG;
+    const int NA = rows->n_agents;
+    GradParams P;
+    ReduceSgdParams Q;
+    P.rows = *rows;
+    int maxn = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const rcmarl_grad_job& q = gjobs[j];
+        if (!q.w || !q.target || !q.time_idx || q.kind < 0 || q.kind > 2 || q.target_stride < 1) return RCMARL_ERR_ARG;
+        if (!sjobs[j].dst || sjobs[j].dst != sjobs[j].src || (const float*)sjobs[j].dst != q.w) return RCMARL_ERR_ARG;
+        const int n = param_count(q.kind == RCMARL_IN_SA ? 3 * NA : 2 * NA, 1);
+        if (sjobs[j].n != n) return RCMARL_ERR_ARG;
+        P.jobs[j] = q;
+        Q.jobs[j] = sjobs[j];
+        if (n + 1 > maxn) maxn = n + 1;
+    }
+    P.partial = (float*)ws;
+    P.n_jobs = n_jobs;
+    P.stride = maxn;
+    Q.partial = (const float*)ws;
+    Q.n_jobs = n_jobs;
+    Q.stride = maxn;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cpc = NA == 5 ? grad_chunks_per_cta<5>(RCMARL_LOSS_MSE) : grad_chunks_per_cta<16>(RCMARL_LOSS_MSE);
+    for (int e = 0; e < epochs; ++e) {
+        for (int b = 0; b < n_times; b += mb_times) {
+            const int cnt = n_times - b < mb_times ? n_times - b : mb_times;
+            const int64_t n_rows = (int64_t)cnt * rows->n_envs;
+            P.rows.n_rows = n_rows;
+            const int64_t nchunks = (n_rows + 63) / 64;
+            const int gy = grid_y_for((nchunks + cpc - 1) / cpc, n_jobs, 1);
+            if ((int64_t)gy * n_jobs * maxn * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
+            for (int j = 0; j < n_jobs; ++j) {
+                P.jobs[j].time_idx = gjobs[j].time_idx + (int64_t)e * n_times + b;
+                Q.jobs[j].coef = lr * 2.0f / (float)n_rows;
+                if (e > 0) Q.jobs[j].loss_out = nullptr;
+            }
+            P.rows.time_idx = P.jobs[0].time_idx;
+            int err = NA == 5 ? launch_grad<5>(P, RCMARL_LOSS_MSE, gy, st) : launch_grad<16>(P, RCMARL_LOSS_MSE, gy, st);
+            if (err) return err;
+            Q.gy = gy;
+            reduce_sgd_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+            RC_CUDA(cudaGetLastError());
+        }
+    }
     return RCMARL_OK;
 }
 

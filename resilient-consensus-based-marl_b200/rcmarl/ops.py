@@ -139,6 +139,16 @@ def sgd_apply(jobs):
     L.check(L.lib().rcmarl_sgd_apply(a, len(a), _stream()), "rcmarl_sgd_apply")
 
 
+def minibatch_sgd(rows, gjobs, sjobs, epochs, n_times, mb_times, lr, ws=None):
+    """Whole mini-batch fit (all epochs, all steps) in one library call (single GPU)."""
+    ga = gjobs if isinstance(gjobs, C.Array) else _arr(L.GradJob, gjobs)
+    sa = sjobs if isinstance(sjobs, C.Array) else _arr(L.SgdJob, sjobs)
+    if ws is None:
+        ws = workspace()
+    L.check(L.lib().rcmarl_minibatch_sgd(C.byref(rows), ga, sa, len(ga), epochs, n_times, mb_times, lr, ws.data_ptr(),
+                                         ws.numel(), _stream()), "rcmarl_minibatch_sgd")
+
+
 def adam_job(theta, m, v, sums, n, grad_scale, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, loss_out=None, loss_coef=0.0,
              loss_accumulate=0):
     j = L.AdamJob()

@@ -354,6 +354,13 @@ class Trainer:
         gj, aj = (L.GradJob * len(gj))(*gj), (L.SgdJob * len(aj))(*aj)
         rows = self._rows(0, 0, perms)
         nC = len(chains)
+        nb_steps = E * nb
+        if self.world == 1:                                # whole fit in one library call (fused reduce + apply)
+            for c in range(nC):
+                gj[c].time_idx = base + 4 * (c * E * T)
+            ops.minibatch_sgd(rows, gj, aj, E, T, self.mb_times, self.fast_lr, self.ws)
+            self.launches += 2 * nb_steps
+            return
         for e in range(E):
             for b in range(nb):
                 cnt = min(self.mb_times, T - b * self.mb_times)
