@@ -34,23 +34,18 @@ struct Track {
         for (int i = 0; i <= H; ++i) { small[i] = INFINITY; large[i] = -INFINITY; }
         sum = 0.f;
     }
+    // Branch-free insertion: with 4 columns per lane and 32 lanes, "some column needs an insert" is true for
+    // practically every row, so a threshold test only adds divergence.  2(2H+1) FMNMX + 1 FADD per element.
     __device__ __forceinline__ void push(float v) {
         sum += v;
-        if (H == 0) {
-            small[0] = fminf(small[0], v);
-            large[0] = fmaxf(large[0], v);
-        } else {
-            if (v < small[H]) {            // threshold fast path: most values touch neither list
-                float c = v;
+        float c = v;
 #pragma unroll
-                for (int i = 0; i <= H; ++i) { float lo = fminf(small[i], c); c = fmaxf(small[i], c); small[i] = lo; }
-            }
-            if (v > large[H]) {
-                float c = v;
+        for (int i = 0; i < H; ++i) { const float lo = fminf(small[i], c); c = fmaxf(small[i], c); small[i] = lo; }
+        small[H] = fminf(small[H], c);
+        c = v;
 #pragma unroll
-                for (int i = 0; i <= H; ++i) { float hi = fmaxf(large[i], c); c = fminf(large[i], c); large[i] = hi; }
-            }
-        }
+        for (int i = 0; i < H; ++i) { const float hi = fmaxf(large[i], c); c = fminf(large[i], c); large[i] = hi; }
+        large[H] = fmaxf(large[H], c);
     }
     __device__ __forceinline__ float finish(float own, int n) const {
         const float lo = fminf(small[H], own);
@@ -64,6 +59,41 @@ struct Track {
         return s / (float)n;
     }
 };
+
+// ---- sorting networks (optimal comparator counts, verified with the 0-1 principle in tools/gen_sortnets.py) ----
+template <bool ASC>
+__device__ __forceinline__ void cswap(float& a, float& b) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = ASC ? lo : hi;
+    b = ASC ? hi : lo;
+}
+template <int N> struct SortNet;
+template <> struct SortNet<1> { template <bool ASC> static __device__ __forceinline__ void run(float (&)[1]) {} };
+template <> struct SortNet<2> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[2]) { cswap<ASC>(a[0], a[1]); } };
+template <> struct SortNet<3> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[3]) { cswap<ASC>(a[0], a[1]); cswap<ASC>(a[1], a[2]); cswap<ASC>(a[0], a[1]); } };
+template <> struct SortNet<4> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[4]) { cswap<ASC>(a[0], a[1]); cswap<ASC>(a[2], a[3]); cswap<ASC>(a[0], a[2]); cswap<ASC>(a[1], a[3]); cswap<ASC>(a[1], a[2]); } };
+template <> struct SortNet<5> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[5]) { cswap<ASC>(a[0], a[1]); cswap<ASC>(a[3], a[4]); cswap<ASC>(a[2], a[4]); cswap<ASC>(a[2], a[3]); cswap<ASC>(a[1], a[4]); cswap<ASC>(a[0], a[3]); cswap<ASC>(a[0], a[2]); cswap<ASC>(a[1], a[3]); cswap<ASC>(a[1], a[2]); } };
+template <> struct SortNet<6> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[6]) { cswap<ASC>(a[1], a[2]); cswap<ASC>(a[4], a[5]); cswap<ASC>(a[0], a[2]); cswap<ASC>(a[3], a[5]); cswap<ASC>(a[0], a[1]); cswap<ASC>(a[3], a[4]); cswap<ASC>(a[2], a[5]); cswap<ASC>(a[0], a[3]); cswap<ASC>(a[1], a[4]); cswap<ASC>(a[2], a[4]); cswap<ASC>(a[1], a[3]); cswap<ASC>(a[2], a[3]); } };
+template <> struct SortNet<7> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[7]) { cswap<ASC>(a[1], a[2]); cswap<ASC>(a[3], a[4]); cswap<ASC>(a[5], a[6]); cswap<ASC>(a[0], a[2]); cswap<ASC>(a[3], a[5]); cswap<ASC>(a[4], a[6]); cswap<ASC>(a[0], a[1]); cswap<ASC>(a[4], a[5]); cswap<ASC>(a[2], a[6]); cswap<ASC>(a[0], a[4]); cswap<ASC>(a[1], a[5]); cswap<ASC>(a[0], a[3]); cswap<ASC>(a[2], a[5]); cswap<ASC>(a[1], a[3]); cswap<ASC>(a[2], a[4]); cswap<ASC>(a[2], a[3]); } };
+template <> struct SortNet<8> { template <bool ASC> static __device__ __forceinline__ void run(float (&a)[8]) { cswap<ASC>(a[0], a[2]); cswap<ASC>(a[1], a[3]); cswap<ASC>(a[4], a[6]); cswap<ASC>(a[5], a[7]); cswap<ASC>(a[0], a[4]); cswap<ASC>(a[1], a[5]); cswap<ASC>(a[2], a[6]); cswap<ASC>(a[3], a[7]); cswap<ASC>(a[0], a[1]); cswap<ASC>(a[2], a[3]); cswap<ASC>(a[4], a[5]); cswap<ASC>(a[6], a[7]); cswap<ASC>(a[2], a[4]); cswap<ASC>(a[3], a[5]); cswap<ASC>(a[1], a[4]); cswap<ASC>(a[3], a[6]); cswap<ASC>(a[1], a[2]); cswap<ASC>(a[3], a[4]); cswap<ASC>(a[5], a[6]); } };
+
+// Group update for H >= 2: the 8 new values of a column are sorted once (19 comparators); the H+1 smallest of
+// {kept smallest (ascending), sorted group} are the element-wise minima against the reversed group head (bitonic
+// half-cleaner), re-sorted with a (H+1)-input network; same for the largest.  ~11 FMNMX per element for H = 4
+// instead of 4H+2 for one-at-a-time insertion.
+template <int H>
+__device__ __forceinline__ void push_group8(Track<H>& t, float (&g)[8]) {
+    constexpr int K = H + 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.sum += g[i];
+    SortNet<8>::run<true>(g);
+#pragma unroll
+    for (int i = 0; i < K; ++i) t.small[i] = fminf(t.small[i], g[K - 1 - i]);
+    SortNet<K>::template run<true>(t.small);
+#pragma unroll
+    for (int i = 0; i < K; ++i) t.large[i] = fmaxf(t.large[i], g[8 - K + i]);
+    SortNet<K>::template run<false>(t.large);
+}
 
 constexpr int CM_UNROLL = 8;
 
@@ -84,8 +114,24 @@ __global__ void __launch_bounds__(256) clip_mean_vec4_kernel(const float* __rest
 #pragma unroll
         for (int u = 0; u < CM_UNROLL; ++u) v[u] = ld_stream(base + (int64_t)(k + u) * rs4);
         if (k == 0) own = v[0];
+        if constexpr (H >= 2) {
+            float g[8];
 #pragma unroll
-        for (int u = 0; u < CM_UNROLL; ++u) { t[0].push(v[u].x); t[1].push(v[u].y); t[2].push(v[u].z); t[3].push(v[u].w); }
+            for (int u = 0; u < 8; ++u) g[u] = v[u].x;
+            push_group8<H>(t[0], g);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = v[u].y;
+            push_group8<H>(t[1], g);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = v[u].z;
+            push_group8<H>(t[2], g);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = v[u].w;
+            push_group8<H>(t[3], g);
+        } else {
+#pragma unroll
+            for (int u = 0; u < CM_UNROLL; ++u) { t[0].push(v[u].x); t[1].push(v[u].y); t[2].push(v[u].z); t[3].push(v[u].w); }
+        }
     }
     for (; k < n; ++k) {
         float4 v = ld_stream(base + (int64_t)k * rs4);
