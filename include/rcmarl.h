@@ -226,6 +226,23 @@ int rcmarl_reward_mix(const float* r, int64_t n_rows, int n_agents, const int32_
                       int n_listed, float scale, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Data parallelism over environment shards: one process per GPU of ONE node.  A bound exchange context
+ * makes rcmarl_grad / rcmarl_team / rcmarl_minibatch_sgd return (and apply) sums over ALL ranks: the per-CTA partials
+ * are reduced, exchanged through NVLink peer memory (CUDA IPC buffers, one-shot all-reduce, rank-ordered summation =>
+ * bitwise identical results on every rank) and, for the mini-batch path, applied -- all inside ONE kernel
+ * (csrc/comm.cuh).  Every rank must issue the same sequence of those calls.  Without a bound context the caller
+ * all-reduces `sums` itself (e.g. NCCL) between rcmarl_grad and the apply.
+ *   create(rank, world <= 8, capacity) -> export a 64-byte IPC handle -> exchange handles out of band (e.g.
+ *   torch.distributed.all_gather_object) -> connect(all handles, rank-major) -> bind. */
+int rcmarl_comm_create(int rank, int world, int64_t max_floats, void** comm_out);
+int rcmarl_comm_handle_bytes(void);
+int rcmarl_comm_export(void* comm, void* handle_out_host);
+int rcmarl_comm_connect(void* comm, const void* handles_host);
+int rcmarl_comm_bind(void* comm);                /* NULL unbinds */
+int rcmarl_comm_error(void* comm);               /* 1 if a peer wait timed out (synchronises the device) */
+int rcmarl_comm_destroy(void* comm);
+
+/* ---------------------------------------------------------------------------
  * K1 + K8.  A block of episodes under a fixed policy for n_envs environments
  * (training/train_agents.py:46-80 + environments/grid_world.py:37-72 +
  * get_action, agents/resilient_CAC_agents.py:208-219): one thread per (episode, env).

@@ -14,6 +14,7 @@
 // training/train_agents.py:86-163 (cited per entry point in include/rcmarl.h).
 #include "common.cuh"
 #include "grad_kernel.cuh"
+#include "comm.cuh"
 
 namespace rcmarl {
 
@@ -132,6 +133,43 @@ __global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__
     } else if (job.loss_out) {
         const float l = job.loss_coef * s;
         *job.loss_out = job.loss_accumulate ? *job.loss_out + l : l;
+    }
+}
+
+// Multi-GPU variant: reduce the CTA partials, exchange over NVLink peer memory (comm.cuh), write the global sums and
+// optionally apply the SGD step -- one kernel, no NCCL call, no host round trip.
+struct ReduceCommParams {
+    const float* partial;
+    float* sums[RCMARL_MAX_JOBS];
+    int32_t n[RCMARL_MAX_JOBS];
+    rcmarl_sgd_job sgd[RCMARL_MAX_JOBS];
+    int32_t n_jobs, stride, gy, fuse_sgd;
+    CommDev comm;
+};
+__global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant__ ReduceCommParams P) {
+    const int j = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nj = P.n[j];
+    const int64_t off = (int64_t)j * P.stride + i;
+    if (i < nj) {
+        float s = 0.f;
+        for (int y = 0; y < P.gy; ++y) s += P.partial[((int64_t)y * P.n_jobs + j) * P.stride + i];
+        P.comm.data[P.comm.rank][(int64_t)(P.comm.seq & 1u) * P.comm.max_floats + off] = s;
+    }
+    comm_publish_and_wait(P.comm, gridDim.x * gridDim.y);
+    if (i < nj) {
+        const float tot = comm_total(P.comm, off);
+        if (P.sums[j]) P.sums[j][i] = tot;
+        if (P.fuse_sgd) {
+            const rcmarl_sgd_job& job = P.sgd[j];
+            if (i < job.n) {
+                const float v = job.src[i];
+                job.dst[i] = i >= job.first ? v - job.coef * tot : v;
+            } else if (i == job.n && job.loss_out) {
+                const float l = job.loss_coef * tot;
+                *job.loss_out = job.loss_accumulate ? *job.loss_out + l : l;
+            }
+        }
     }
 }
 
@@ -434,7 +472,15 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
     Q.n_jobs = n_jobs;
     Q.stride = maxn;
     Q.gy = gy;
-    reduce_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+    if (comm_bound()) {
+        ReduceCommParams C;
+        if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
+        C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = maxn; C.gy = gy; C.fuse_sgd = 0;
+        for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
+        reduce_comm_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(C);
+    } else {
+        reduce_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+    }
     RC_CUDA(cudaGetLastError());
     return RCMARL_OK;
 }
@@ -485,7 +531,20 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
             int err = NA == 5 ? launch_grad<5>(P, RCMARL_LOSS_MSE, gy, st) : launch_grad<16>(P, RCMARL_LOSS_MSE, gy, st);
             if (err) return err;
             Q.gy = gy;
-            reduce_sgd_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+            if (comm_bound()) {
+                ReduceCommParams C;
+                if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
+                C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = maxn; C.gy = gy; C.fuse_sgd = 1;
+                for (int j = 0; j < n_jobs; ++j) {
+                    C.sums[j] = nullptr;
+                    C.n[j] = Q.jobs[j].n + 1;
+                    C.sgd[j] = Q.jobs[j];
+                    C.sgd[j].coef = lr * 2.0f / ((float)n_rows * (float)C.comm.world);   // global batch
+                }
+                reduce_comm_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(C);
+            } else {
+                reduce_sgd_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+            }
             RC_CUDA(cudaGetLastError());
         }
     }
@@ -528,7 +587,15 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
         Q.n_jobs = n_jobs;
         Q.stride = TEAM_N;
         Q.gy = gy;
-        reduce_kernel<<<dim3(1, n_jobs), 256, 0, st>>>(Q);
+        if (comm_bound()) {
+            ReduceCommParams C;
+            if (!comm_next(&C.comm, (int64_t)n_jobs * TEAM_N)) return RCMARL_ERR_ARG;
+            C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = TEAM_N; C.gy = gy; C.fuse_sgd = 0;
+            for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
+            reduce_comm_kernel<<<dim3(1, n_jobs), 256, 0, st>>>(C);
+        } else {
+            reduce_kernel<<<dim3(1, n_jobs), 256, 0, st>>>(Q);
+        }
         RC_CUDA(cudaGetLastError());
     }
     return RCMARL_OK;

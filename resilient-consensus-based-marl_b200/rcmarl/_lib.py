@@ -90,6 +90,13 @@ SYMBOLS = [
                                        C.c_int, C.c_float, c_fp, C.c_int64, c_fp]),
     ("rcmarl_team", C.c_int, [C.POINTER(Rows), C.POINTER(TeamJob), C.c_int, c_fp, C.c_int64, c_fp]),
     ("rcmarl_reward_mix", C.c_int, [c_fp, C.c_int64, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_float, c_fp, c_fp]),
+    ("rcmarl_comm_create", C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    ("rcmarl_comm_handle_bytes", C.c_int, []),
+    ("rcmarl_comm_export", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("rcmarl_comm_connect", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("rcmarl_comm_bind", C.c_int, [C.c_void_p]),
+    ("rcmarl_comm_error", C.c_int, [C.c_void_p]),
+    ("rcmarl_comm_destroy", C.c_int, [C.c_void_p]),
     ("rcmarl_rollout", C.c_int, [C.POINTER(RolloutArgs), c_fp]),
     ("rcmarl_env_step", C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
 ]

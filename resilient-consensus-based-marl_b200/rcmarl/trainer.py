@@ -12,6 +12,7 @@ rows for ever; parameters are replicated; the only exchange is one all-reduce
 of the packed UNSCALED gradient sums per SGD / Adam / projection step.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -99,10 +100,19 @@ class Trainer:
         self.launches = 0                                 # kernels launched by this engine (bench: gpu_launches)
         self.profile = None                               # bench.py: {"fit_grad": [(start_evt, end_evt), ...], ...}
         self.h2d_bytes = 4 * sum(x.numel() for x in (self.actor, self.critic, self.tr, self.critic_local))
+        # data parallel: exchange gradient sums inside the reduction kernels over NVLink peer memory (csrc/comm.cuh);
+        # RCMARL_PEER_COMM=0 selects one NCCL all-reduce per step instead
+        self.comm = None
+        if self.world > 1 and os.environ.get("RCMARL_PEER_COMM", "1") != "0":
+            from .comm import PeerComm
+            self.comm = PeerComm(self.rank, self.world, self.group)
         self.d2h_bytes = 0
 
     # ------------------------------------------------------------------ helpers
     def _allreduce(self, t):
+        """Sum the packed gradient sums over ranks -- unless the bound peer-memory context already did it in-kernel."""
+        if self.comm is not None:
+            return t
         return dist_util.allreduce_sums(t, self.world, self.group)
 
     def _timed(self, name, fn, *args):
@@ -152,7 +162,7 @@ class Trainer:
         self.episodes_done += n_ep
         stats = torch.stack([est.mean(dim=1), ret.mean(dim=1)])          # logging only
         if self.world > 1:
-            self._allreduce(stats)
+            dist_util.allreduce_sums(stats, self.world, self.group)     # logging only (NCCL)
             stats /= self.world
         stats = stats.cpu().numpy()
         self.d2h_bytes += stats.nbytes
@@ -355,7 +365,7 @@ class Trainer:
         rows = self._rows(0, 0, perms)
         nC = len(chains)
         nb_steps = E * nb
-        if self.world == 1:                                # whole fit in one library call (fused reduce + apply)
+        if self.world == 1 or self.comm is not None:       # whole fit in one library call (fused reduce [+ exchange] + apply)
             for c in range(nC):
                 gj[c].time_idx = base + 4 * (c * E * T)
             ops.minibatch_sgd(rows, gj, aj, E, T, self.mb_times, self.fast_lr, self.ws)
