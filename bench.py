@@ -166,7 +166,25 @@ def cpu_reference_arm(cfg, rounds, seed=0):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (e.g. NCCL's version banner)
+    was diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -210,7 +228,7 @@ def main():
                                       sample=desc + " per step; NumPy (BLAS threads = all cores) restatement of the "
                                       "reference loop -- faster than the original TF-2.4 code path (no Keras retracing)"),
                     e2e=dict(value=v, unit="agent-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -333,7 +351,7 @@ def main():
                     vs_baseline=None, dtype="f32", data="synthetic", config=config, clocks=clk, e2e=e2e,
                     gpu_launches=launches, roofline=roof, consensus_roofline=cons, cpu_baseline=cpu,
                     breakdown_ms=breakdown, update_rounds_per_s=args.steps / (ms / 1000.0))
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
