@@ -97,62 +97,6 @@ struct GradParams {
     int32_t stride;
 };
 
-// Blackwell packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): two IEEE fp32 FMAs per issue slot.
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pack2(float lo, float hi) {
-    f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-    f2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
-// z[r][:] = b + x[r] W for R rows at once: every broadcast weight quad (uniform LDS.128) feeds 2*R FFMA2;
-// outputs are packed as pairs of adjacent hidden units.
-template <int K, int R>
-__device__ __forceinline__ void dense20_rows(const float* __restrict__ sW, const float* __restrict__ sb,
-                                             const float (&x)[R][K], float (&h)[R][HID]) {
-    f2 hp[R][HID / 2];
-#pragma unroll
-    for (int q = 0; q < HID / 4; ++q) {
-        const float4 v = reinterpret_cast<const float4*>(sb)[q];
-#pragma unroll
-        for (int r = 0; r < R; ++r) { hp[r][2 * q] = pack2(v.x, v.y); hp[r][2 * q + 1] = pack2(v.z, v.w); }
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const float4* w = reinterpret_cast<const float4*>(sW + k * HID);
-        f2 xk[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) xk[r] = pack2(x[r][k], x[r][k]);
-#pragma unroll
-        for (int q = 0; q < HID / 4; ++q) {
-            const float4 v = w[q];
-            const f2 w0 = pack2(v.x, v.y), w1 = pack2(v.z, v.w);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                hp[r][2 * q] = fma2(xk[r], w0, hp[r][2 * q]);
-                hp[r][2 * q + 1] = fma2(xk[r], w1, hp[r][2 * q + 1]);
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int j = 0; j < HID / 2; ++j) {
-            float a, b;
-            unpack2(hp[r][j], a, b);
-            h[r][2 * j] = lrelu(a);
-            h[r][2 * j + 1] = lrelu(b);
-        }
-}
-
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }

@@ -43,12 +43,16 @@ struct ValuesParams {
     rcmarl_value_job jobs[RCMARL_MAX_JOBS];
 };
 
+// value of R = 2 rows per thread: every broadcast weight quad feeds both rows (see grad_kernel.cuh)
 template <int NA, int DIN>
-__device__ __forceinline__ float value_term(const rcmarl_rows& R, const float* sw, int kind, int64_t row) {
-    float x[DIN], h1[HID], h2[HID];
-    load_x<NA, DIN>(R, kind, row, x);
-    features<DIN>(sw, x, h1, h2);
-    return head1<DIN>(sw, h2);
+__device__ __forceinline__ void value_term2(const rcmarl_rows& R, const float* sw, int kind, const int64_t (&row)[2],
+                                            float (&v)[2]) {
+    float x[2][DIN], h1[2][HID], h2[2][HID];
+    load_x<NA, DIN>(R, kind, row[0], x[0]);
+    load_x<NA, DIN>(R, kind, row[1], x[1]);
+    features_rows<DIN, 2>(sw, x, h1, h2);
+    v[0] = head1<DIN>(sw, h2[0]);
+    v[1] = head1<DIN>(sw, h2[1]);
 }
 
 template <int NA>
@@ -82,18 +86,28 @@ __global__ void __launch_bounds__(256) values_kernel(const __grid_constant__ Val
         __syncthreads();
         stage_weights(smem, job.w[t], kind == RCMARL_IN_SA ? param_count(3 * NA, 1) : param_count(2 * NA, 1));
         __syncthreads();
-        for (int64_t it = 0; it < n_iter; ++it) {
-            int64_t m = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-            if (m < R.n_rows) {
-                int64_t row = row_of(R, m);
-                float v = (kind == RCMARL_IN_SA) ? value_term<NA, 3 * NA>(R, smem, kind, row)
-                                                  : value_term<NA, 2 * NA>(R, smem, kind, row);
+        for (int64_t it = 0; it < n_iter; it += 2) {          // two rows per thread and iteration
+            int64_t m[2], row[2];
+            bool live[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                m[r] = (it + r) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                live[r] = (it + r) < n_iter && m[r] < R.n_rows;
+                row[r] = row_of(R, live[r] ? m[r] : 0);
+            }
+            if (!live[0]) continue;
+            float v[2];
+            if (kind == RCMARL_IN_SA) value_term2<NA, 3 * NA>(R, smem, kind, row, v);
+            else value_term2<NA, 2 * NA>(R, smem, kind, row, v);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!live[r]) continue;
                 float acc;
                 if (t == 0)
-                    acc = job.add ? job.add_scale * __ldg(job.add + row * job.add_stride + job.add_off) : 0.f;
+                    acc = job.add ? job.add_scale * __ldg(job.add + row[r] * job.add_stride + job.add_off) : 0.f;
                 else
-                    acc = job.out[row];
-                job.out[row] = fmaf(job.scale[t], v, acc);
+                    acc = job.out[row[r]];
+                job.out[row[r]] = fmaf(job.scale[t], v[r], acc);
             }
         }
     }
@@ -185,7 +199,9 @@ struct TeamParams {
 };
 constexpr int TEAM_N = HID + 2;  // 20 weights + bias numerators + diagnostic loss
 
-template <int NA, int DIN>
+// MAXN: compile-time bound on the neighbour count (4 / 8 / 16) so that the estimate vector and the rank-counting
+// order statistics stay in registers without paying for 16 x 16 predicated compares when n_in = 4
+template <int NA, int DIN, int MAXN>
 __device__ __forceinline__ void team_body(const TeamParams& P, const rcmarl_team_job& job, float* smem) {
     constexpr int NP = param_count(DIN, 1);
     const rcmarl_rows& R = P.rows;
@@ -203,41 +219,58 @@ __device__ __forceinline__ void team_body(const TeamParams& P, const rcmarl_team
     for (int j = 0; j < TEAM_N; ++j) acc[j] = 0.f;
     const int64_t stride = (int64_t)gridDim.y * blockDim.x;
     const int64_t n_iter = (R.n_rows + stride - 1) / stride;
-    for (int64_t it = 0; it < n_iter; ++it) {
-        const int64_t m = it * stride + (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-        if (m < R.n_rows) {
-            const int64_t row = row_of(R, m);
-            float x[DIN], h1[HID], phi[HID];
-            load_x<NA, DIN>(R, job.kind, row, x);
-            features<DIN>(sw, x, h1, phi);
-            float agg;
-            if (job.agg_in) {
-                agg = __ldg(job.agg_in + row);
-            } else {
-                float est[RCMARL_MAX_NEIGHBOURS];
+    for (int64_t it = 0; it < n_iter; it += 2) {                   // two rows per thread and iteration
+        int64_t row[2];
+        bool live[2];
 #pragma unroll
-                for (int k = 0; k < RCMARL_MAX_NEIGHBOURS; ++k) {
-                    est[k] = 0.f;
-                    if (k < job.n_in) {
-                        const float* hk = heads + k * 24;
-                        float s = hk[HID];
+        for (int r = 0; r < 2; ++r) {
+            const int64_t m = (it + r) * stride + (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+            live[r] = (it + r) < n_iter && m < R.n_rows;
+            row[r] = row_of(R, live[r] ? m : 0);
+        }
+        if (!live[0]) continue;
+        float phi[2][HID];
+        {
+            float x[2][DIN], h1[2][HID];
+            load_x<NA, DIN>(R, job.kind, row[0], x[0]);
+            load_x<NA, DIN>(R, job.kind, row[1], x[1]);
+            features_rows<DIN, 2>(sw, x, h1, phi);
+        }
+        float agg[2];
+        if (job.agg_in) {
+            agg[0] = __ldg(job.agg_in + row[0]);
+            agg[1] = __ldg(job.agg_in + row[1]);
+        } else {
+            float est[2][MAXN];
 #pragma unroll
-                        for (int j = 0; j < HID; ++j) s = fmaf(phi[j], hk[j], s);
-                        est[k] = s;
-                    }
+            for (int k = 0; k < MAXN; ++k) {
+                est[0][k] = 0.f;
+                est[1][k] = 0.f;
+                if (k < job.n_in) {
+                    const float* hk = heads + k * 24;
+                    float s0 = hk[HID], s1 = hk[HID];
+#pragma unroll
+                    for (int j = 0; j < HID; ++j) { s0 = fmaf(phi[0][j], hk[j], s0); s1 = fmaf(phi[1][j], hk[j], s1); }
+                    est[0][k] = s0;
+                    est[1][k] = s1;
                 }
-                agg = clip_mean_small<RCMARL_MAX_NEIGHBOURS>(est, job.n_in, job.H);
             }
-            if (job.agg_out) job.agg_out[row] = agg;
+            agg[0] = clip_mean_small<MAXN>(est[0], job.n_in, job.H);
+            agg[1] = clip_mean_small<MAXN>(est[1], job.n_in, job.H);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!live[r]) continue;
+            if (job.agg_out) job.agg_out[row[r]] = agg[r];
             if (job.sums) {
-                const float pred = head1<DIN>(sw, phi);
+                const float pred = head1<DIN>(sw, phi[r]);
                 float nrm = 1.f;
 #pragma unroll
-                for (int j = 0; j < HID; ++j) nrm = fmaf(phi[j], phi[j], nrm);
-                const float err = agg - pred;
+                for (int j = 0; j < HID; ++j) nrm = fmaf(phi[r][j], phi[r][j], nrm);
+                const float err = agg[r] - pred;
                 const float c = err / nrm;
 #pragma unroll
-                for (int j = 0; j < HID; ++j) acc[j] = fmaf(c, phi[j], acc[j]);
+                for (int j = 0; j < HID; ++j) acc[j] = fmaf(c, phi[r][j], acc[j]);
                 acc[HID] += c;
                 acc[HID + 1] = fmaf(err, c, acc[HID + 1]);
             }
@@ -261,11 +294,17 @@ __device__ __forceinline__ void team_body(const TeamParams& P, const rcmarl_team
 }
 
 template <int NA>
-__global__ void __launch_bounds__(256) team_kernel(const __grid_constant__ TeamParams P) {
+__global__ void __launch_bounds__(128) team_kernel(const __grid_constant__ TeamParams P) {
     extern __shared__ __align__(16) float smem[];
     const rcmarl_team_job& job = P.jobs[blockIdx.x];
-    if (job.kind == RCMARL_IN_SA) team_body<NA, 3 * NA>(P, job, smem);
-    else team_body<NA, 2 * NA>(P, job, smem);
+    const bool sa = job.kind == RCMARL_IN_SA;
+    if (job.n_in <= 4) {
+        if (sa) team_body<NA, 3 * NA, 4>(P, job, smem); else team_body<NA, 2 * NA, 4>(P, job, smem);
+    } else if (job.n_in <= 8) {
+        if (sa) team_body<NA, 3 * NA, 8>(P, job, smem); else team_body<NA, 2 * NA, 8>(P, job, smem);
+    } else {
+        if (sa) team_body<NA, 3 * NA, 16>(P, job, smem); else team_body<NA, 2 * NA, 16>(P, job, smem);
+    }
 }
 
 // ============================================================================================
@@ -349,7 +388,7 @@ static int launch_values(const ValuesParams& P, int n_jobs, cudaStream_t st) {
                                                    ? param_count(3 * NA, 1) : param_count(2 * NA, NACT));
     if (set_smem(values_kernel<NA>, smem)) return RCMARL_ERR_CUDA;
     int64_t gx = (P.rows.n_rows + 255) / 256;
-    const int64_t cap = (int64_t)sm_count_cached() * 8;
+    const int64_t cap = (int64_t)sm_count_cached() * 2;   // 2 resident CTAs per SM (126 registers x 256 threads)
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     values_kernel<NA><<<dim3((unsigned)gx, n_jobs), 256, smem, st>>>(P);
@@ -391,7 +430,7 @@ template <int NA>
 static int launch_team(const TeamParams& P, int gy, cudaStream_t st) {
     const size_t smem = sizeof(float) * (round4(param_count(3 * NA, 1)) + RCMARL_MAX_NEIGHBOURS * 24 + 8 * TEAM_N);
     if (set_smem(team_kernel<NA>, smem)) return RCMARL_ERR_CUDA;
-    team_kernel<NA><<<dim3(P.n_jobs, gy), 256, smem, st>>>(P);
+    team_kernel<NA><<<dim3(P.n_jobs, gy), 128, smem, st>>>(P);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -572,7 +611,7 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
         Q.sums[j] = q.sums;
         Q.n[j] = q.sums ? TEAM_N : 0;
     }
-    const int gy = grid_y_for((rows->n_rows + 255) / 256, n_jobs, 4);
+    const int gy = grid_y_for((rows->n_rows + 255) / 256, n_jobs, 3);   // 128 threads x 2 rows; 3 CTAs/SM resident
     if (any_sums) {
         if (!ws || (int64_t)gy * n_jobs * TEAM_N * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
     }
