@@ -255,7 +255,11 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
         }
         __syncwarp();
         // ---------------- phase 2: 8x8 register tile per lane, NG rows per step ----------------
-#pragma unroll 2
+#ifndef RCMARL_PH2_UNROLL
+#define RCMARL_PH2_UNROLL 4
+#endif
+        constexpr int kPh2Unroll = RCMARL_PH2_UNROLL;
+#pragma unroll kPh2Unroll
         for (int it = 0; it < L::ROWS / L::NG; ++it) {
             const float* rp = wt + (it * L::NG + grp) * L::RS;
             const float4 a0 = *reinterpret_cast<const float4*>(rp + aoff);
