@@ -415,6 +415,42 @@ class Trainer:
             ops.adam_apply(aj)
             self.launches += 3
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self, include_buffer=True):
+        """Everything needed to continue training bit-for-bit: parameters, Keras-Adam slots and step counts, the
+        replay buffer, the episode counter that keys the Philox streams and the shuffle generator.  (The reference
+        saves only the final weights, main.py:119-121; optimiser state and buffer are lost there -- SURVEY 5.)"""
+        T = self.t_filled * self.N
+        sd = dict(version=1, labels=list(self.labels), n_envs=self.N, t_filled=self.t_filled,
+                  episodes_done=self.episodes_done, adam_t=list(self.adam_t), perm_rng=self._perm_gen.get_state(),
+                  actor=self.actor.cpu(), critic=self.critic.cpu(), tr=self.tr.cpu(), critic_local=self.critic_local.cpu(),
+                  adam_m=self.adam_m.cpu(), adam_v=self.adam_v.cpu())
+        if include_buffer:
+            sd.update(sa=self.sa[:T].cpu(), ns=self.ns[:T].cpu(), r=self.r[:T].cpu())
+        return sd
+
+    def load_state_dict(self, sd):
+        if list(sd["labels"]) != list(self.labels) or int(sd["n_envs"]) != self.N:
+            raise L.RcmarlError("checkpoint was written for a different agent set / environment count")
+        for name in ("actor", "critic", "tr", "critic_local", "adam_m", "adam_v"):
+            getattr(self, name).copy_(sd[name])
+        self.adam_t = [int(t) for t in sd["adam_t"]]
+        self.episodes_done = int(sd["episodes_done"])
+        self._perm_gen.set_state(sd["perm_rng"])
+        self.t_filled = 0
+        if "sa" in sd:
+            T = int(sd["t_filled"]) * self.N
+            if T > self.sa.shape[0]:
+                raise L.RcmarlError("checkpointed replay buffer does not fit")
+            self.sa[:T].copy_(sd["sa"]); self.ns[:T].copy_(sd["ns"]); self.r[:T].copy_(sd["r"])
+            self.t_filled = int(sd["t_filled"])
+
+    def save(self, path, include_buffer=True):
+        torch.save(self.state_dict(include_buffer), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+
     def trim(self):
         """Keep the newest `buffer_size` time rows (train_agents.py:158-163): chunked, non-overlapping
         device-to-device copies (pure data movement)."""

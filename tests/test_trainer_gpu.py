@@ -120,3 +120,24 @@ def test_batched_update_round_matches_oracle(labels, common, H):
         np.testing.assert_array_equal(tr.ns[:tr.t_filled * N].cpu().numpy().reshape(-1, 5, 2), NS)
     for i in range(5):
         close_w(tr.get_weights(i), agents[i].get_parameters())
+
+
+def test_checkpoint_resume_is_bitwise(tmp_path):
+    """state_dict / load_state_dict: weights, Adam slots, buffer, Philox episode counter and shuffle stream -- a resumed
+    run continues exactly like the uninterrupted one (the reference cannot resume optimiser state or buffer)."""
+    need_gpu()
+    from rcmarl.trainer import Trainer
+    w, desired, labels = pretrained()
+    kw = dict(labels=labels, in_nodes=IN_NODES, weights=w, desired=desired, n_envs=32, gamma=0.9, H=1, fast_lr=0.01,
+              slow_lr=0.002, max_ep_len=6, n_ep_fixed=7, n_epochs=2, buffer_size=60, seed=9)
+    a = Trainer(**kw)
+    a.rollout_block(); a.update_round()
+    a.save(tmp_path / "ckpt.pt")
+    a.rollout_block(); a.update_round()
+    b = Trainer(**kw)
+    b.load(tmp_path / "ckpt.pt")
+    assert b.t_filled == 42 and b.adam_t == [1] * 5
+    b.rollout_block(); b.update_round()
+    for name in ("actor", "critic", "tr", "critic_local", "adam_m", "adam_v", "sa", "ns", "r"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert a.adam_t == b.adam_t and a.episodes_done == b.episodes_done
