@@ -304,7 +304,12 @@ def main():
         mac = n_coop * ((d_c * 20 + 400 + 20) + (d_c * 20 + 400 + 20 + 400 + 20 + 20) +
                         (d_t * 20 + 400 + 20) + (d_t * 20 + 400 + 20 + 400 + 20 + 20))
         flops = 2.0 * mac * rows_fit
-        fp32_peak = 2 * 128 * 148 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+        try:
+            fp32_peak = json.load(open(os.path.join(ROOT, "profiles", "r01_fp32_peak.json")))["fp32_tflops"]
+            fp32_src = "measured on this pool (FFMA2 issue-rate loop, profiles/r01_peak_rates.md)"
+        except Exception:
+            fp32_peak = 2 * 128 * 148 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+            fp32_src = "nominal 2*128 lanes*148 SMs*max SM clock"
         roof = dict(kernel="grad_kernel<5,MSE> (rcmarl_grad, full-batch fit step)", bound="hbm",
                     achieved=alg_bytes / (fit_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                     frac=alg_bytes / (fit_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=grad_traffic(args.workload),
@@ -313,7 +318,7 @@ def main():
                     note="this kernel is FP32-FMA bound (350 FLOP/B); see fp32",
                     fp32=dict(achieved=flops / (fit_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
                               frac=flops / (fit_ms * 1e-3) / 1e12 / fp32_peak,
-                              peak_source="nominal 2*128 lanes*148 SMs*max SM clock (no measured FP32 peak provided)",
+                              peak_source=fp32_src,
                               algorithmic_flop_per_launch=flops))
     breakdown = {k: dict(ms_total=float(np.sum(v)), calls=len(v)) for k, v in prof.items()}
 
