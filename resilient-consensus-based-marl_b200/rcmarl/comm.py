@@ -22,9 +22,13 @@ class PeerComm:
         L.check(lib.rcmarl_comm_export(h, buf), "rcmarl_comm_export")
         gathered = [None] * world
         dist.all_gather_object(gathered, bytes(buf.raw), group=group)
-        L.check(lib.rcmarl_comm_connect(h, b"".join(gathered)), "rcmarl_comm_connect")
+        status = lib.rcmarl_comm_connect(h, b"".join(gathered))
         torch.cuda.synchronize()
-        dist.barrier(group=group)                     # every rank has mapped every buffer before first use
+        dist.barrier(group=group)                     # every rank has mapped (or failed to map) every buffer
+        if status != 0:
+            lib.rcmarl_comm_destroy(h)
+            self.handle = None
+            L.check(status, "rcmarl_comm_connect")
         L.check(lib.rcmarl_comm_bind(h), "rcmarl_comm_bind")
         self.bound = True
 

@@ -104,11 +104,29 @@ class Trainer:
         # RCMARL_PEER_COMM=0 selects one NCCL all-reduce per step instead
         self.comm = None
         if self.world > 1 and os.environ.get("RCMARL_PEER_COMM", "1") != "0":
-            from .comm import PeerComm
-            self.comm = PeerComm(self.rank, self.world, self.group)
-        self.d2h_bytes = 0
+            self.comm = self._try_peer_comm()
 
     # ------------------------------------------------------------------ helpers
+    def _try_peer_comm(self):
+        """Set up the peer-memory exchange on every rank, or on none: the ranks agree (MIN all-reduce of a success
+        flag) so that a box without IPC / peer access falls back to the NCCL path consistently instead of deadlocking."""
+        import torch.distributed as dist
+        from .comm import PeerComm
+        comm, ok = None, 1
+        try:
+            comm = PeerComm(self.rank, self.world, self.group)
+        except Exception as ex:                                      # noqa: BLE001 -- any failure means "use NCCL"
+            ok = 0
+            if self.rank == 0:
+                print(f"[rcmarl] peer-memory exchange unavailable ({ex}); using NCCL all-reduce", flush=True)
+        flag = torch.tensor([ok], device=self.dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if comm is not None:
+                comm.close()
+            return None
+        return comm
+
     def _allreduce(self, t):
         """Sum the packed gradient sums over ranks -- unless the bound peer-memory context already did it in-kernel."""
         if self.comm is not None:
