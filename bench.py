@@ -20,7 +20,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -224,8 +223,6 @@ def main():
         import torch
         torch.set_num_threads(ncores)
         vals = []
-        for _ in range(max(args.warmup, 0) and 0):
-            pass
         t_all = time.perf_counter()
         for _ in range(args.steps):
             v, dt, desc = cpu_reference_arm(cfg, rounds=1)
@@ -249,7 +246,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from rcmarl.trainer import Trainer
-    from rcmarl import ops, _lib
+    from rcmarl import ops
 
     tr = Trainer(rank=rank, world=world, group=group, seed=1234, **cfg)
 
@@ -383,7 +380,6 @@ def e2e_arm(cfg, args, rank, world, tr):
     buffer / weights / permutations and device->host reads of logs, losses and weights are inside the timed region."""
     import torch
     try:
-        import training.train_agents as training
         from rcmarl import api
     except Exception as ex:                                   # pragma: no cover
         return dict(value=None, unit="agent-updates/s", error=f"public API unavailable: {ex!r}")

@@ -34,7 +34,7 @@ import tensorflow as tf                                   # noqa: E402  (the fac
 from tensorflow import keras                              # noqa: E402
 from environments.grid_world import Grid_World            # noqa: E402  (reference, verbatim)
 from agents.resilient_CAC_agents import RPBCAC_agent      # noqa: E402
-from agents.adversarial_CAC_agents import Malicious_CAC_agent, Greedy_CAC_agent, Faulty_CAC_agent  # noqa: E402
+from agents.adversarial_CAC_agents import Malicious_CAC_agent   # noqa: E402
 import training.train_agents as ref_training              # noqa: E402
 
 RAW = os.path.join(REF, "simulation_results", "raw_data")

@@ -9,12 +9,10 @@ Same constructor and method names, argument meaning and mutation conventions as 
   actor_update              one Keras-Adam step weighted by the team TD error (:86-101)
 Tensors may be NumPy arrays, torch tensors or facade Tensors; they are moved to the GPU.  Calling these methods one
 by one is the compatibility path; training.train_agents.train_RPBCAC drives the same kernels fused over all agents."""
-import numpy as np
 import torch
 
 from tensorflow import keras
 from tensorflow.keras import Tensor
-from rcmarl import _lib as L
 from rcmarl import agent_ops as A
 from rcmarl import nets, ops
 

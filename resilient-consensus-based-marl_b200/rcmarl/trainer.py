@@ -11,7 +11,6 @@ Data-parallel: each rank owns n_envs environments and their buffer
 rows for ever; parameters are replicated; the only exchange is one all-reduce
 of the packed UNSCALED gradient sums per SGD / Adam / projection step.
 """
-import ctypes as C
 import os
 
 import numpy as np
@@ -85,7 +84,7 @@ class Trainer:
         self.tdt = torch.zeros(NA, rows, **f32)          # critic TD targets (train_agents.py / res..py:114-115)
         n_mal = sum(l == MALICIOUS for l in self.labels)
         self.tdt_local = torch.zeros(max(n_mal, 1), rows if n_mal else 1, **f32)
-        self.delta = torch.zeros(NA, self.block * self.N, **f32)   # TD errors of the actor window (indexed from 0)
+        self.delta = torch.zeros(NA, rows, **f32)        # TD errors (actor window), indexed by absolute buffer row
         self.r_coop = torch.zeros(rows, **f32)
         self.neg_r_coop = torch.zeros(rows if n_mal else 1, **f32)
         # reduction outputs (contiguous so that one all-reduce covers a whole launch)
@@ -100,6 +99,7 @@ class Trainer:
         self.launches = 0                                 # kernels launched by this engine (bench: gpu_launches)
         self.profile = None                               # bench.py: {"fit_grad": [(start_evt, end_evt), ...], ...}
         self.h2d_bytes = 4 * sum(x.numel() for x in (self.actor, self.critic, self.tr, self.critic_local))
+        self.d2h_bytes = 0
         # data parallel: exchange gradient sums inside the reduction kernels over NVLink peer memory (csrc/comm.cuh);
         # RCMARL_PEER_COMM=0 selects one NCCL all-reduce per step instead
         self.comm = None
@@ -326,16 +326,13 @@ class Trainer:
         rows_act = self._rows(a0, Ta * N)
         d_jobs = []
         for i in range(NA):
-            out = self.delta[i]
-            # delta is indexed by absolute row in the kernels: shift the base so that row a0 lands on delta[i][0]
-            view = _ShiftedView(out, a0)
             if lab[i] == COOP:                                             # res..py:95-98
-                d_jobs.append(_value_job_shifted(view, [(self.tr[i], L.IN_SA, 1.0), (self.critic[i], L.IN_NS, self.gamma),
-                                                        (self.critic[i], L.IN_S, -1.0)]))
+                d_jobs.append(ops.value_job(self.delta[i], [(self.tr[i], L.IN_SA, 1.0), (self.critic[i], L.IN_NS, self.gamma),
+                                                            (self.critic[i], L.IN_S, -1.0)]))
             else:                                                          # adversarial:38-40,113-115,221-223
                 cw = self.critic_local[i] if lab[i] == MALICIOUS else self.critic[i]
-                d_jobs.append(_value_job_shifted(view, [(cw, L.IN_NS, self.gamma), (cw, L.IN_S, -1.0)],
-                                                 add=r_col[i], add_stride=NA))
+                d_jobs.append(ops.value_job(self.delta[i], [(cw, L.IN_NS, self.gamma), (cw, L.IN_S, -1.0)],
+                                            add=r_col[i], add_stride=NA))
         ops.values(rows_act, arr(L.ValueJob, d_jobs))
         self.launches += 1
         Bag = Ta * N * self.world
@@ -343,7 +340,7 @@ class Trainer:
             gj, aj = [], []
             for n, i in enumerate(coop):
                 self.adam_t[i] += 1
-                gj.append(_grad_job_shifted(self.actor[i], _ShiftedView(self.delta[i], a0), self.sums_actor[n], L.IN_S, i))
+                gj.append(ops.grad_job(self.actor[i], self.delta[i], self.sums_actor[n], L.IN_S, action_agent=i))
                 aj.append(ops.adam_job(self.actor[i], self.adam_m[i], self.adam_v[i], self.sums_actor[n], self.PA, 1.0 / Bag,
                                        ops.keras_adam_lr_t(self.slow_lr[i], self.adam_t[i]), loss_out=self.loss_a[i:i + 1],
                                        loss_coef=1.0 / Bag))
@@ -414,8 +411,7 @@ class Trainer:
         rows = self._rows(a0, 0, perms)
         gj = []
         for n, i in enumerate(adv):
-            gj.append(_grad_job_shifted(self.actor[i], _ShiftedView(self.delta[i], a0), self.sums_actor[n], L.IN_S, i,
-                                        time_idx=perms))
+            gj.append(ops.grad_job(self.actor[i], self.delta[i], self.sums_actor[n], L.IN_S, action_agent=i, time_idx=perms))
             self.loss_a[i:i + 1].zero_()
         gj = (L.GradJob * len(gj))(*gj)
         for b in range(nb):
@@ -484,22 +480,3 @@ class Trainer:
                 buf[done * N:(done + n) * N].copy_(buf[(done + q) * N:(done + q + n) * N])
                 done += n
         self.t_filled = keep
-
-
-class _ShiftedView:
-    """A per-row array stored from index 0 but addressed by absolute buffer row in the kernels:
-    the pointer handed to the C ABI is moved back by `row0` elements (never dereferenced below row0)."""
-
-    def __init__(self, tensor, row0):
-        self.tensor, self.row0 = tensor, row0
-
-    def data_ptr(self):
-        return self.tensor.data_ptr() - 4 * self.row0
-
-
-def _value_job_shifted(view, terms, add=None, add_stride=1):
-    return ops.value_job(view, terms, add=add, add_stride=add_stride)
-
-
-def _grad_job_shifted(w, view, sums, kind, agent, time_idx=None):
-    return ops.grad_job(w, view, sums, kind, action_agent=agent, time_idx=time_idx)
