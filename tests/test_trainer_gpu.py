@@ -141,3 +141,36 @@ def test_checkpoint_resume_is_bitwise(tmp_path):
     for name in ("actor", "critic", "tr", "critic_local", "adam_m", "adam_v", "sa", "ns", "r"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert a.adam_t == b.adam_t and a.episodes_done == b.episodes_done
+
+
+def test_c3_shape_update_round_matches_oracle():
+    """BASELINE config 3 shape at test size: 10x10 grid, 16 cooperative agents, H = 2, circulant in-neighbourhoods of 6
+    (SURVEY 8d), batched environments -- the n_agents = 16 instantiation of every kernel through the trainer."""
+    need_gpu()
+    from rcmarl.trainer import Trainer
+    from rcmarl import nets
+    rs = np.random.RandomState(11)
+    NA, N, T1, gamma, H = 16, 3, 40, 0.9, 2
+    labels = ['Cooperative'] * NA
+    in_nodes = [[(i + k) % NA for k in range(6)] for i in range(NA)]
+    w = [[nets.glorot_uniform(32, 5, rs), nets.glorot_uniform(32, 1, rs), nets.glorot_uniform(48, 1, rs)] for _ in range(NA)]
+    desired = rs.randint(0, 10, size=(NA, 2))
+    agents = [O.RPBCACOracleAgent(w[i][0], w[i][1], w[i][2], 0.002, 0.01, gamma, H=H, dtype=np.float64) for i in range(NA)]
+    tr = Trainer(labels=labels, in_nodes=in_nodes, weights=w, desired=desired, n_envs=N, nrow=10, ncol=10, gamma=gamma, H=H,
+                 fast_lr=0.01, slow_lr=0.002, max_ep_len=8, n_ep_fixed=5, n_epochs=2, buffer_size=100)
+    B = T1 * N
+    pos = rs.randint(0, 10, size=(B, NA, 2))
+    npos = np.clip(pos + rs.randint(-1, 2, size=pos.shape), 0, 9)
+    mean, std = 4.5, np.std(np.arange(10))
+    s = ((pos - mean) / std).astype(np.float32)
+    ns = ((npos - mean) / std).astype(np.float32)
+    a = rs.randint(0, 5, size=(B, NA, 1)).astype(np.float32)
+    r = (-rs.randint(0, 19, size=(B, NA, 1)) / 5.0).astype(np.float32)
+    want = O.update_round(agents, labels, in_nodes, s, ns, a, r, n_envs=N, n_epochs=2, n_actor_steps=40,
+                          common_reward=False, perm_source=lambda T: np.arange(T))
+    tr.load_rows(s, ns, a, r)
+    got = tr.update_round()
+    for k in ("critic_loss", "TR_loss", "actor_loss"):
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-3, atol=2e-5, err_msg=k)
+    for i in range(NA):
+        close_w(tr.get_weights(i), agents[i].get_parameters())
