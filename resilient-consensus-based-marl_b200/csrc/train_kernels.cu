@@ -113,6 +113,25 @@ __global__ void __launch_bounds__(256) values_kernel(const __grid_constant__ Val
     }
 }
 
+// Deterministic sum over the gy CTA partials of one parameter, parallel over the 8 warps of a 256-thread block:
+// block b of job j owns parameters [32 b, 32 b + 32); warp w adds y = w, w + 8, ... (coalesced 128-byte rows), the
+// eight warp sums are combined in warp order.  Returns the total in the threads of warp 0 (others return 0).
+__device__ __forceinline__ float block_partial_sum(const float* __restrict__ partial, int n_jobs, int stride, int gy,
+                                                   int j, int i, bool valid, float* sh /* [8][32] */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float s = 0.f;
+    if (valid)
+        for (int y = warp; y < gy; y += 8) s += partial[((int64_t)y * n_jobs + j) * stride + i];
+    sh[warp * 32 + lane] = s;
+    __syncthreads();
+    float tot = 0.f;
+    if (warp == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += sh[w * 32 + lane];
+    }
+    return tot;
+}
+
 // sums[j][i] = sum_y partial[y][j][i], y ascending (deterministic)
 struct ReduceParams {
     const float* partial;
@@ -121,12 +140,12 @@ struct ReduceParams {
     int32_t n_jobs, stride, gy;
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ ReduceParams P) {
+    __shared__ float sh[256];
     const int j = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n[j]) return;
-    float s = 0.f;
-    for (int y = 0; y < P.gy; ++y) s += P.partial[((int64_t)y * P.n_jobs + j) * P.stride + i];
-    P.sums[j][i] = s;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+    const bool valid = i < P.n[j];
+    const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, j, i, valid, sh);
+    if (threadIdx.x < 32 && valid) P.sums[j][i] = s;
 }
 
 // fused: sums[j][i] = sum_y partial[y][j][i]; theta = theta - coef * sums (mini-batch SGD step, single GPU)
@@ -136,11 +155,12 @@ struct ReduceSgdParams {
     int32_t n_jobs, stride, gy;
 };
 __global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__ ReduceSgdParams P) {
+    __shared__ float sh[256];
     const rcmarl_sgd_job& job = P.jobs[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > job.n) return;
-    float s = 0.f;
-    for (int y = 0; y < P.gy; ++y) s += P.partial[((int64_t)y * P.n_jobs + blockIdx.y) * P.stride + i];
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+    const bool valid = i <= job.n;
+    const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, blockIdx.y, i, valid, sh);
+    if (threadIdx.x >= 32 || !valid) return;
     if (i < job.n) {
         const float v = job.src[i];
         job.dst[i] = i >= job.first ? v - job.coef * s : v;
@@ -161,17 +181,17 @@ struct ReduceCommParams {
     CommDev comm;
 };
 __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant__ ReduceCommParams P) {
+    __shared__ float sh[256];
     const int j = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const int nj = P.n[j];
+    const bool valid = i < nj;
     const int64_t off = (int64_t)j * P.stride + i;
-    if (i < nj) {
-        float s = 0.f;
-        for (int y = 0; y < P.gy; ++y) s += P.partial[((int64_t)y * P.n_jobs + j) * P.stride + i];
+    const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, j, i, valid, sh);
+    if (threadIdx.x < 32 && valid)
         P.comm.data[P.comm.rank][(int64_t)(P.comm.seq & 1u) * P.comm.max_floats + off] = s;
-    }
     comm_publish_and_wait(P.comm, gridDim.x * gridDim.y);
-    if (i < nj) {
+    if (threadIdx.x < 32 && valid) {
         const float tot = comm_total(P.comm, off);
         if (P.sums[j]) P.sums[j][i] = tot;
         if (P.fuse_sgd) {
@@ -516,9 +536,9 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
         if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
         C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = maxn; C.gy = gy; C.fuse_sgd = 0;
         for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
-        reduce_comm_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(C);
+        reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
     } else {
-        reduce_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+        reduce_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(Q);
     }
     RC_CUDA(cudaGetLastError());
     return RCMARL_OK;
@@ -580,9 +600,9 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
                     C.sgd[j] = Q.jobs[j];
                     C.sgd[j].coef = lr * 2.0f / ((float)n_rows * (float)C.comm.world);   // global batch
                 }
-                reduce_comm_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(C);
+                reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
             } else {
-                reduce_sgd_kernel<<<dim3((maxn + 255) / 256, n_jobs), 256, 0, st>>>(Q);
+                reduce_sgd_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(Q);
             }
             RC_CUDA(cudaGetLastError());
         }
@@ -631,9 +651,9 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
             if (!comm_next(&C.comm, (int64_t)n_jobs * TEAM_N)) return RCMARL_ERR_ARG;
             C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = TEAM_N; C.gy = gy; C.fuse_sgd = 0;
             for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
-            reduce_comm_kernel<<<dim3(1, n_jobs), 256, 0, st>>>(C);
+            reduce_comm_kernel<<<dim3((TEAM_N + 31) / 32, n_jobs), 256, 0, st>>>(C);
         } else {
-            reduce_kernel<<<dim3(1, n_jobs), 256, 0, st>>>(Q);
+            reduce_kernel<<<dim3((TEAM_N + 31) / 32, n_jobs), 256, 0, st>>>(Q);
         }
         RC_CUDA(cudaGetLastError());
     }
