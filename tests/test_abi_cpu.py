@@ -73,3 +73,16 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_product_tree_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under resilient-consensus-based-marl_b200/ may import or execute it."""
+    prod = os.path.join(ROOT, "resilient-consensus-based-marl_b200")
+    offenders = []
+    for dirpath, _dirs, files in os.walk(prod):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|rpbcac_oracle|tf_facade", txt, re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
