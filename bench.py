@@ -352,6 +352,7 @@ def main():
     # ---- e2e: the reference-facing API (training.train_agents.train_RPBCAC) with HOST buffers
     e2e = None
     if not args.no_e2e:
+        barrier()                                             # ranks enter the end-to-end arm together
         e2e = e2e_arm(cfg, args, rank, world, tr)
 
     cpu = None

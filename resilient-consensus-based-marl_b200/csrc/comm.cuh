@@ -57,9 +57,10 @@ __device__ __forceinline__ void comm_publish_and_wait(const CommDev& c, unsigned
         const long long t0 = clock64();
         for (int p = 0; p < c.world; ++p) {
             while ((int32_t)(ld_acquire_sys(c.flags[c.rank] + p) - c.seq) < 0) {
-                if (clock64() - t0 > 8000000000LL) {     // ~4 s: a peer died; fail loudly instead of hanging the GPU
+                if (clock64() - t0 > 120000000000LL) {   // ~60 s: a peer died; fail loudly instead of hanging the GPU
                     *c.error = 1u;
-                    break;
+                    __threadfence_system();
+                    __trap();                            // surfaces as a CUDA error at the next synchronisation
                 }
             }
         }
