@@ -72,21 +72,47 @@ struct TileLayout {
     }
 };
 
-constexpr int GRAD_SMEM_BUDGET = 226 * 1024;   // one CTA per SM (up to 255 registers per thread)
+constexpr int GRAD_SMEM_BUDGET = 227 * 1024;   // one CTA per SM (up to 255 registers per thread)
+// staged input rows: 64 buffer rows of sa (3*NA floats) or ns (2*NA floats); the staging buffer is sized for sa rows:
+// 3*NA == DIN for the team-reward net (DIN = 3*NA) and 3*DIN/2 for critic / actor (DIN = 2*NA)
+__host__ __device__ constexpr int stage_floats_per_row(int din, bool is_sa_net) { return is_sa_net ? din : (3 * din) / 2; }
 
 // warps per CTA: as many 64-row tiles as fit next to the staged weights, at most 8
-template <int DIN, int NOUT>
+// Bulk-copy input staging costs 64 x 3*NA x 4 bytes of shared memory per warp.  At n_agents = 5 (3.8 KB per warp) it fits
+// next to 8 tiles; at n_agents = 16 it would cut the CTA from 6 to 4 warps, so those instantiations keep per-lane loads.
+__host__ __device__ constexpr bool grad_use_tma(int na) { return na <= 5; }
+
+template <int DIN, int NOUT, bool SA_NET>
 constexpr int grad_warps_for() {
     using L = TileLayout<DIN, NOUT>;
-    const int avail = GRAD_SMEM_BUDGET - 4 * (round4(param_count(DIN, NOUT)) + 16);
-    const int n = avail / (4 * L::ROWS * L::RS);
+    const int na = SA_NET ? DIN / 3 : DIN / 2;
+    const int avail = GRAD_SMEM_BUDGET - 4 * (round4(param_count(DIN, NOUT)) + 16) - 128;
+    const int n = avail / (4 * L::ROWS * L::RS + (grad_use_tma(na) ? 4 * L::ROWS * stage_floats_per_row(DIN, SA_NET) : 0));
     return n > 8 ? 8 : n;
 }
 template <int NA, int LOSS>
 constexpr int grad_warps() {
-    if (LOSS == RCMARL_LOSS_CE) return grad_warps_for<2 * NA, NACT>();
-    const int a = grad_warps_for<3 * NA, 1>(), b = grad_warps_for<2 * NA, 1>();
+    if (LOSS == RCMARL_LOSS_CE) return grad_warps_for<2 * NA, NACT, false>();
+    const int a = grad_warps_for<3 * NA, 1, true>(), b = grad_warps_for<2 * NA, 1, false>();
     return a < b ? a : b;
+}
+
+// ---- 1-D bulk copy (TMA engine, SASS UBLKCP) of the next chunk's input rows into a warp-private staging buffer ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
 }
 
 struct GradParams {
@@ -112,9 +138,39 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     float* tiles = smem + round4(NP);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* wt = tiles + warp * (L::ROWS * L::RS);
+    constexpr int SROW = 3 * NA;                                     // staged row = one sa row (ns rows are shorter)
+    constexpr int SWARP = grad_use_tma(NA) ? L::ROWS * SROW : 0;      // staging floats per warp
+    float* stage = tiles + GRAD_WARPS * (L::ROWS * L::RS) + warp * SWARP;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + GRAD_WARPS * (L::ROWS * L::RS) + GRAD_WARPS * SWARP) + warp;
 
     stage_weights(sw, job.w, NP);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+
+    // Input staging by the TMA engine: the 64 rows of a chunk are one contiguous, 16-byte aligned span of sa / ns whenever
+    // the chunk is full and (contiguous row mode, or gathered mode with n_envs % 64 == 0); lane 0 issues one 1-D bulk copy
+    // per chunk, completion is tracked by the warp's mbarrier; other chunks fall back to per-lane loads.
+    const bool from_ns = (DIN == 2 * NA) && job.kind == RCMARL_IN_NS;
+    const int rowf = from_ns ? 2 * NA : 3 * NA;
+    const float* in_base = from_ns ? Rw.ns : Rw.sa;
+    const bool gather_ok = grad_use_tma(NA) && ((Rw.time_idx == nullptr) || (Rw.n_envs % L::ROWS == 0));
+    auto stage_src = [&](int64_t c, const float*& src) -> bool {
+        if (!gather_ok || (c + 1) * L::ROWS > Rw.n_rows) return false;
+        src = in_base + row_of(Rw, c * L::ROWS) * rowf;
+        return (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    };
+    uint32_t phase = 0;
+    bool staged = false;
+    const int64_t cstep = (int64_t)gridDim.y * GRAD_WARPS;
+    {
+        const int64_t c0 = (int64_t)blockIdx.y * GRAD_WARPS + warp;
+        const float* src = nullptr;
+        if (c0 * L::ROWS < Rw.n_rows) staged = stage_src(c0, src);
+        if (staged && lane == 0) bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
+    }
 
     // phase-2 assignment of this lane: tile `tile`, row group `grp`
     const bool busy = lane < L::NG * L::NT;
@@ -131,7 +187,7 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     float loss = 0.f;
 
     const int64_t nchunks = (Rw.n_rows + L::ROWS - 1) / L::ROWS;
-    for (int64_t c = (int64_t)blockIdx.y * GRAD_WARPS + warp; c < nchunks; c += (int64_t)gridDim.y * GRAD_WARPS) {
+    for (int64_t c = (int64_t)blockIdx.y * GRAD_WARPS + warp; c < nchunks; c += cstep) {
         // ---------------- phase 1: two rows per lane (lane, lane + 32 of the chunk) ----------------
         {
             bool live[R];
@@ -145,8 +201,30 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
             float h1[R][HID], h2[R][HID];
             {
                 float x[R][DIN];
+                if (staged) {                                              // rows of this chunk were bulk-copied
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    const int skip = (DIN == 2 * NA && !from_ns) ? 1 : 0;  // s out of sa: skip the action slots
 #pragma unroll
-                for (int r = 0; r < R; ++r) load_x<NA, DIN>(Rw, job.kind, row[r], x[r]);
+                    for (int r = 0; r < R; ++r) {
+                        const float* sp = stage + (lane + 32 * r) * rowf;
+#pragma unroll
+                        for (int k = 0; k < DIN; ++k) x[r][k] = sp[k + skip * (k >> 1)];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) load_x<NA, DIN>(Rw, job.kind, row[r], x[r]);
+                }
+                __syncwarp();
+                {                                                          // prefetch the next chunk of this warp
+                    const int64_t c2 = c + cstep;
+                    const float* src = nullptr;
+                    staged = (c2 < nchunks) && stage_src(c2, src);
+                    if (staged && lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async writes
+                        bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
+                    }
+                }
                 dense20_rows<DIN, R>(sw, sw + off_b1(DIN), x, h1);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -342,12 +420,14 @@ __global__ void __launch_bounds__(32 * grad_warps<NA, LOSS>(), 1) grad_kernel(co
     }
 }
 
-template <int DIN, int NOUT, int NW>
+template <int NA, int DIN, int NOUT, int NW>
 constexpr int grad_smem_floats() {
     using L = TileLayout<DIN, NOUT>;
-    const int tiles = NW * L::ROWS * L::RS;
-    const int red = NW * 32 * 64 + NW * (HID + 2);
-    return round4(param_count(DIN, NOUT)) + (tiles > red ? tiles : red) + 16;
+    constexpr int tiles = NW * L::ROWS * L::RS;
+    constexpr int red = NW * 32 * 64 + NW * (HID + 2);
+    static_assert(tiles >= red, "the CTA reduction buffer reuses the tile region");
+    constexpr int stage = (grad_use_tma(NA) ? NW * L::ROWS * 3 * NA : 0) + 2 * NW + 8;   // staged rows + one mbarrier per warp
+    return round4(param_count(DIN, NOUT)) + tiles + stage + 16;
 }
 
 }  // namespace rcmarl

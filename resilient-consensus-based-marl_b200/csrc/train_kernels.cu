@@ -419,9 +419,10 @@ static int launch_values(const ValuesParams& P, int n_jobs, cudaStream_t st) {
 template <int NA>
 static int launch_grad(GradParams& P, int loss_mode, int gy, cudaStream_t st) {
     constexpr int NWM = grad_warps<NA, RCMARL_LOSS_MSE>(), NWC = grad_warps<NA, RCMARL_LOSS_CE>();
-    constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<3 * NA, 1, NWM>() > grad_smem_floats<2 * NA, 1, NWM>()
-                                                     ? grad_smem_floats<3 * NA, 1, NWM>() : grad_smem_floats<2 * NA, 1, NWM>());
-    constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<2 * NA, NACT, NWC>();
+    constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<NA, 3 * NA, 1, NWM>() > grad_smem_floats<NA, 2 * NA, 1, NWM>()
+                                                     ? grad_smem_floats<NA, 3 * NA, 1, NWM>() : grad_smem_floats<NA, 2 * NA, 1, NWM>());
+    constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<NA, 2 * NA, NACT, NWC>();
+    static_assert(smem_mse <= 227 * 1024 && smem_ce <= 227 * 1024, "grad kernel exceeds the 227 KB shared-memory limit");
     static bool attr_ce = false, attr_mse = false;     // opt-in to > 48 KB dynamic shared memory once per process
     if (loss_mode == RCMARL_LOSS_CE) {
         if (!attr_ce) {
