@@ -18,7 +18,7 @@ struct CommHost {
 static CommHost* g_bound = nullptr;
 CommHost* comm_bound() { return g_bound; }
 
-static size_t data_bytes(const CommHost* c) { return sizeof(float) * 2 * (size_t)c->max_floats; }
+static size_t data_bytes(const CommHost* c) { return sizeof(float) * 2 * (size_t)c->world * (size_t)c->max_floats; }
 static size_t total_bytes(const CommHost* c) { return data_bytes(c) + sizeof(uint32_t) * (COMM_MAX_WORLD + 8); }
 
 bool comm_next(CommDev* out, int64_t need_floats) {

@@ -1,16 +1,16 @@
 // comm.cuh -- one-shot all-reduce over NVLink peer memory, fused into the reduction / apply kernels
 // (data-parallel env shards).  Every rank owns one cudaMalloc'ed exchange buffer that all peers map
-// through CUDA IPC:  [ data: 2 slots x max_floats | flags: one uint32 per peer | CTA arrival counter ].
-// Protocol for step `seq` (identical call sequence on every rank):
-//   1. each CTA writes its part of the rank's local sums into the rank's OWN slot (seq & 1), fences system-wide and
-//      bumps the arrival counter; the last CTA to arrive publishes `seq` into flags[rank] of EVERY peer
-//      (st.release.sys over NVLink);
+// through CUDA IPC:  [ data: 2 slots x world sources x max_floats | flags: one uint32 per peer | CTA arrival counter ].
+// Push protocol for step `seq` (identical call sequence on every rank):
+//   1. each thread STORES its part of the rank's local sums into slot (seq & 1), source `rank`, of EVERY peer's buffer
+//      (fire-and-forget stores over NVLink), fences system-wide, and the CTA bumps the arrival counter; the last CTA to
+//      arrive publishes `seq` into flags[rank] of every peer (st.release.sys);
 //   2. every CTA waits until its LOCAL flags show `seq` for all peers (local polling, ld.acquire.sys);
-//   3. every thread pulls its element from all peers' slots (ld.cv over NVLink) and sums in rank order, so all ranks
-//      obtain bitwise identical totals (the replicated parameters never diverge); the SGD update can be applied in
-//      the same kernel.
-// Double buffering by `seq & 1` is sufficient: a rank can only reach step s+2 after every peer has published s+1,
-// which a peer does only after it finished reading step s.
+//   3. every thread reads the world values of its element from its OWN buffer (no NVLink round trip) and sums them in
+//      rank order, so all ranks obtain bitwise identical totals (the replicated parameters never diverge); the SGD
+//      update can be applied in the same kernel.
+// Double buffering by `seq & 1` is sufficient: a rank can only reach step s+2 (and overwrite slot s & 1 at its peers)
+// after every peer has published s+1, which a peer does only after it finished reading step s.
 #pragma once
 #include <stdint.h>
 
@@ -68,10 +68,24 @@ __device__ __forceinline__ void comm_publish_and_wait(const CommDev& c, unsigned
     __syncthreads();
 }
 
+// element `offset` of source rank `src` in slot (seq & 1) of a buffer
+__device__ __forceinline__ int64_t comm_index(const CommDev& c, int src, int64_t offset) {
+    return ((int64_t)(c.seq & 1u) * c.world + src) * c.max_floats + offset;
+}
+// step 1: push this rank's value to every peer (own buffer included)
+__device__ __forceinline__ void comm_push(const CommDev& c, int64_t offset, float v) {
+    const int64_t idx = comm_index(c, c.rank, offset);
+    for (int p = 0; p < c.world; ++p) c.data[p][idx] = v;
+}
+// step 3: rank-ordered sum of the values all ranks pushed into OUR buffer
 __device__ __forceinline__ float comm_total(const CommDev& c, int64_t offset) {
+    float v[COMM_MAX_WORLD];
+#pragma unroll
+    for (int p = 0; p < COMM_MAX_WORLD; ++p)
+        v[p] = p < c.world ? ld_peer(c.data[c.rank] + comm_index(c, p, offset)) : 0.f;
     float tot = 0.f;
-    const int64_t slot = (int64_t)(c.seq & 1u) * c.max_floats;
-    for (int p = 0; p < c.world; ++p) tot += ld_peer(c.data[p] + slot + offset);
+#pragma unroll
+    for (int p = 0; p < COMM_MAX_WORLD; ++p) tot += v[p];   // rank order: identical bits on every rank
     return tot;
 }
 

@@ -188,8 +188,7 @@ __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant_
     const bool valid = i < nj;
     const int64_t off = (int64_t)j * P.stride + i;
     const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, j, i, valid, sh);
-    if (threadIdx.x < 32 && valid)
-        P.comm.data[P.comm.rank][(int64_t)(P.comm.seq & 1u) * P.comm.max_floats + off] = s;
+    if (threadIdx.x < 32 && valid) comm_push(P.comm, off, s);
     comm_publish_and_wait(P.comm, gridDim.x * gridDim.y);
     if (threadIdx.x < 32 && valid) {
         const float tot = comm_total(P.comm, off);
