@@ -33,6 +33,11 @@ __host__ __device__ constexpr int off_W3(int din) { return din * HID + 2 * HID +
 __host__ __device__ constexpr int off_b3(int din, int nout) { return off_W3(din) + HID * nout; }
 __host__ __device__ constexpr int round4(int n) { return (n + 3) & ~3; }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
+// its prologue while its predecessor drains; it must not touch the predecessor's outputs before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float lrelu(float z) { return z > 0.f ? z : SLOPE * z; }
 // derivative expressed through the activation output (sign(h) == sign(z), slope > 0);
 // tf.nn.leaky_relu passes alpha*g at z == 0

@@ -143,11 +143,12 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     float* stage = tiles + GRAD_WARPS * (L::ROWS * L::RS) + warp * SWARP;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + GRAD_WARPS * (L::ROWS * L::RS) + GRAD_WARPS * SWARP) + warp;
 
-    stage_weights(sw, job.w, NP);
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();                       // everything above overlaps the tail of the previous kernel (PDL)
+    stage_weights(sw, job.w, NP);
     __syncthreads();
 
     // Input staging by the TMA engine: the 64 rows of a chunk are one contiguous, 16-byte aligned span of sa / ns whenever

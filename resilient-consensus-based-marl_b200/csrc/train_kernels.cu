@@ -141,6 +141,7 @@ struct ReduceParams {
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ ReduceParams P) {
     __shared__ float sh[256];
+    pdl_launch_dependents();     // the next grad kernel may start its prologue; it waits (pdl_wait) before reading
     const int j = blockIdx.y;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const bool valid = i < P.n[j];
@@ -156,6 +157,7 @@ struct ReduceSgdParams {
 };
 __global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__ ReduceSgdParams P) {
     __shared__ float sh[256];
+    pdl_launch_dependents();     // the next grad kernel may start its prologue; it waits (pdl_wait) before reading
     const rcmarl_sgd_job& job = P.jobs[blockIdx.y];
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const bool valid = i <= job.n;
@@ -182,6 +184,7 @@ struct ReduceCommParams {
 };
 __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant__ ReduceCommParams P) {
     __shared__ float sh[256];
+    pdl_launch_dependents();     // the next grad kernel may start its prologue; it waits (pdl_wait) before reading
     const int j = blockIdx.y;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const int nj = P.n[j];
@@ -423,18 +426,30 @@ static int launch_grad(GradParams& P, int loss_mode, int gy, cudaStream_t st) {
     constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<NA, 2 * NA, NACT, NWC>();
     static_assert(smem_mse <= 227 * 1024 && smem_ce <= 227 * 1024, "grad kernel exceeds the 227 KB shared-memory limit");
     static bool attr_ce = false, attr_mse = false;     // opt-in to > 48 KB dynamic shared memory once per process
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P.n_jobs, gy);
+    cfg.stream = st;
+    cfg.attrs = &pdl;
+    cfg.numAttrs = 1;
     if (loss_mode == RCMARL_LOSS_CE) {
         if (!attr_ce) {
             if (set_smem(grad_kernel<NA, RCMARL_LOSS_CE>, smem_ce)) return RCMARL_ERR_CUDA;
             attr_ce = true;
         }
-        grad_kernel<NA, RCMARL_LOSS_CE><<<dim3(P.n_jobs, gy), 32 * NWC, smem_ce, st>>>(P);
+        cfg.blockDim = dim3(32 * NWC);
+        cfg.dynamicSmemBytes = smem_ce;
+        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel<NA, RCMARL_LOSS_CE>, P));
     } else {
         if (!attr_mse) {
             if (set_smem(grad_kernel<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
             attr_mse = true;
         }
-        grad_kernel<NA, RCMARL_LOSS_MSE><<<dim3(P.n_jobs, gy), 32 * NWM, smem_mse, st>>>(P);
+        cfg.blockDim = dim3(32 * NWM);
+        cfg.dynamicSmemBytes = smem_mse;
+        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel<NA, RCMARL_LOSS_MSE>, P));
     }
     RC_CUDA(cudaGetLastError());
     return 0;
