@@ -49,6 +49,9 @@ __device__ __forceinline__ bool mbar_wait_timeout(uint64_t* bar, uint32_t parity
 template <int ROWS>
 __device__ __forceinline__ int canon(int r, int k) { return (k >> 2) * (ROWS * 4) + r * 4 + (k & 3); }
 
+// mode 0: A from shared memory (SS);  mode 1: A from TMEM (TS): every thread stores its own row's hi / lo values with
+// tcgen05.st.32x32b (lane = row, consecutive registers = consecutive columns) -- the thread-per-row layout of the MLP kernels
+template <int mode>
 __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                                              int reps, int* status, long long* cycles) {
     __shared__ __align__(128) float a_hi[M * K], a_lo[M * K], b_hi[N * K], b_lo[N * K];
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                                     // one warp allocates 32 TMEM columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic smem writes -> async-proxy (MMA) reads
@@ -81,23 +84,70 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
     const uint32_t idesc = make_idesc(M, N);
+    const uint32_t tmem_ahi = tmem + 32, tmem_alo = tmem + 32 + K;       // columns 32..55 and 56..79
+    if (mode == 1) {
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (int ks = 0; ks < NKSTEP; ++ks) {
+            uint32_t h[8], l[8];
+            for (int u = 0; u < 8; ++u) {
+                const float v = Ablk[tid * K + ks * 8 + u], hv = to_tf32(v);
+                h[u] = __float_as_uint(hv);
+                l[u] = __float_as_uint(v - hv);
+            }
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         ::"r"(tmem_ahi + lane_base + ks * 8), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         ::"r"(tmem_alo + lane_base + ks * 8), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     long long t0 = 0, t1 = 0;
     bool ok = true;
     uint32_t parity = 0;
     if (tid == 0) {
+        // descriptors are loop invariants: the timed loop is nothing but the 9 tcgen05.mma issues per repetition
+        uint64_t dah[NKSTEP], dal[NKSTEP], dbh[NKSTEP], dbl[NKSTEP];
+        for (int ks = 0; ks < NKSTEP; ++ks) {
+            const uint32_t aoff = ks * 2 * (M * 16), boff = ks * 2 * (N * 16);           // two 16-byte K chunks per step
+            dah[ks] = make_desc(smem_u32(a_hi) + aoff, M * 16, 128); dal[ks] = make_desc(smem_u32(a_lo) + aoff, M * 16, 128);
+            dbh[ks] = make_desc(smem_u32(b_hi) + boff, N * 16, 128); dbl[ks] = make_desc(smem_u32(b_lo) + boff, N * 16, 128);
+        }
         t0 = clock64();
+#pragma unroll 1
         for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
             for (int ks = 0; ks < NKSTEP; ++ks) {
-                const uint32_t aoff = ks * 2 * (M * 16), boff = ks * 2 * (N * 16);       // two 16-byte K chunks per step
-                const uint64_t dah = make_desc(smem_u32(a_hi) + aoff, M * 16, 128), dal = make_desc(smem_u32(a_lo) + aoff, M * 16, 128);
-                const uint64_t dbh = make_desc(smem_u32(b_hi) + boff, N * 16, 128), dbl = make_desc(smem_u32(b_lo) + boff, N * 16, 128);
                 const uint32_t acc0 = (ks > 0) ? 1u : 0u;                                  // first MMA of a rep overwrites D
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem), "l"(dah), "l"(dbh), "r"(idesc), "r"(acc0) : "memory");
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem), "l"(dal), "l"(dbh), "r"(idesc), "r"(1u) : "memory");
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem), "l"(dah), "l"(dbl), "r"(idesc), "r"(1u) : "memory");
+                if (mode == 2) {
+                    // three INDEPENDENT accumulators (TMEM columns 0, 32, 64), issue interleaved: is the ~47-cycle interval of
+                    // modes 0/1 a dependency latency on the shared accumulator or the pipe's throughput for this shape?
+#pragma unroll
+                    for (int which = 0; which < 3; ++which)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const uint64_t da = which == 1 ? dal[ks] : dah[ks], db = which == 2 ? dbl[ks] : dbh[ks];
+                            const uint32_t acc = (ks > 0 || which > 0) ? 1u : 0u;
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                         ::"r"(tmem + 32 * t), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                        }
+                } else if (mode == 1) {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "r"(tmem_ahi + ks * 8), "l"(dbh[ks]), "r"(idesc), "r"(acc0) : "memory");
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "r"(tmem_alo + ks * 8), "l"(dbh[ks]), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "r"(tmem_ahi + ks * 8), "l"(dbl[ks]), "r"(idesc), "r"(1u) : "memory");
+                } else {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "l"(dah[ks]), "l"(dbh[ks]), "r"(idesc), "r"(acc0) : "memory");
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "l"(dal[ks]), "l"(dbh[ks]), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "l"(dah[ks]), "l"(dbl[ks]), "r"(idesc), "r"(1u) : "memory");
+                }
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -120,7 +170,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
     if (tid == 0) {
         if (!ok) atomicExch(status, 1);
         if (blockIdx.x == 0) *cycles = t1 - t0;
@@ -145,15 +195,23 @@ int main() {
     cudaMemcpy(dB, hB, sizeof(float) * N * K, cudaMemcpyHostToDevice);
     cudaMemset(dstatus, 0, sizeof(int));
     cudaMemset(dC, 0, sizeof(float) * blocks_max * M * N);
-    probe<<<1, 128>>>(dA, dB, dC, 1, dstatus, dcyc);
-    cudaError_t e = cudaDeviceSynchronize();
+    cudaError_t e;
     int st = 0;
+    float* hC = (float*)malloc(sizeof(float) * M * N);
+    const int reps = 4000;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int mode = 0; mode < 3; ++mode) {
+    printf("---- mode %d: %s\n", mode, mode == 2 ? "SS, three independent accumulators issued interleaved (27 MMAs per repetition)"
+                                       : mode ? "A operand from TMEM (TS, tcgen05.st by the row-owning thread)" : "A operand from shared memory (SS)");
+    cudaMemset(dC, 0, sizeof(float) * blocks_max * M * N);
+    if (mode == 2) probe<2><<<1, 128>>>(dA, dB, dC, 1, dstatus, dcyc); else if (mode) probe<1><<<1, 128>>>(dA, dB, dC, 1, dstatus, dcyc); else probe<0><<<1, 128>>>(dA, dB, dC, 1, dstatus, dcyc);
+    e = cudaDeviceSynchronize();
     cudaMemcpy(&st, dstatus, sizeof(int), cudaMemcpyDeviceToHost);
     printf("correctness launch: %s, timeout flag %d\n", cudaGetErrorString(e), st);
     if (e != cudaSuccess || st) return 1;
-    float* hC = (float*)malloc(sizeof(float) * M * N);
     cudaMemcpy(hC, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost);
-    double worst = 0, worst_tf32 = 0;
+    double worst = 0;
     for (int r = 0; r < M; ++r)
         for (int n = 0; n < N; ++n) {
             double ref = 0;
@@ -161,14 +219,10 @@ int main() {
             worst = fmax(worst, fabs(ref - hC[r * N + n]));
         }
     printf("3xTF32 128x32x24 tile vs fp64: max abs err %.3e (plain fp32 accumulation would give ~1e-6; 1xTF32 ~1e-3)\n", worst);
-    (void)worst_tf32;
     // issue-rate: many repetitions of the 9-MMA group on every SM
-    const int reps = 4000;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
     for (int blocks : {1, 148}) {
         cudaEventRecord(a);
-        probe<<<blocks, 128>>>(dA, dB, dC, reps, dstatus, dcyc);
+        if (mode == 2) probe<2><<<blocks, 128>>>(dA, dB, dC, reps, dstatus, dcyc); else if (mode) probe<1><<<blocks, 128>>>(dA, dB, dC, reps, dstatus, dcyc); else probe<0><<<blocks, 128>>>(dA, dB, dC, reps, dstatus, dcyc);
         cudaEventRecord(b);
         e = cudaDeviceSynchronize();
         float ms;
@@ -176,10 +230,12 @@ int main() {
         cudaMemcpy(&st, dstatus, sizeof(int), cudaMemcpyDeviceToHost);
         long long cyc = 0;
         cudaMemcpy(&cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost);
-        const double flop = 2.0 * M * N * KSTEP * 9.0 * reps * blocks;
+        const double n_mma = (mode == 2 ? 27.0 : 9.0);
+        const double flop = 2.0 * M * N * KSTEP * n_mma * reps * blocks;
         printf("%3d CTA(s): %s timeout %d  %.3f ms  %.1f TFLOP/s dense tf32 (= %.1f TFLOP/s useful fp32 after the 3x split), "
                "%.1f cycles per 128x32x8 MMA\n", blocks, cudaGetErrorString(e), st, ms, flop / (ms * 1e-3) / 1e12,
-               flop / 3.0 / (ms * 1e-3) / 1e12, (double)cyc / (9.0 * reps));
+               flop / 3.0 / (ms * 1e-3) / 1e12, (double)cyc / (n_mma * reps));
+    }
     }
     return 0;
 }
