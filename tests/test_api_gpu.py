@@ -165,3 +165,43 @@ def test_train_rpbcac_drop_in_contract(n_envs, tmp_path):
     assert np.array_equal(agents[0].critic.get_weights()[0], back[0][1][0])
     tr = training.train_RPBCAC.last_trainer
     assert tr.t_filled == 96 + 4 * 6 and tr.adam_t[0] == 2 and tr.adam_t[4] == 2
+
+
+def test_greedy_and_faulty_agent_methods_match_oracle():
+    """Per-method API of the two remaining adversaries (agents/adversarial_CAC_agents.py:5-72,184-275) against the
+    oracle with injected fit permutations."""
+    need_gpu()
+    from agents.adversarial_CAC_agents import Greedy_CAC_agent, Faulty_CAC_agent
+    from oracle import rpbcac_oracle as O
+    z = load("ref_methods.npz")
+    w, _, _ = pretrained()
+    s, ns, a, r = z["s"], z["ns"], z["a"], z["r"]
+    sa = np.concatenate([s, a], -1)
+    B = s.shape[0]
+    rs = np.random.RandomState(5)
+    perms = [rs.permutation(B) for _ in range(21)]
+    it = iter(perms)
+    g = Greedy_CAC_agent(*build_models(w[3]), slow_lr=0.002, fast_lr=0.01, gamma=0.9)
+    g.perm_source = lambda T: next(it)
+    x, xl = g.TR_update_local(sa, r[:, 3])
+    y, yl = g.critic_update_local(s, ns, r[:, 3])
+    al = g.actor_update(s, ns, r[:, 3], a[:, 3])
+    og = O.GreedyOracleAgent(w[3][0], w[3][1], w[3][2], 0.002, 0.01, 0.9, dtype=np.float64)
+    ox, oxl = og.TR_update_local(sa, r[:, 3], perms[0:10])
+    oy, oyl = og.critic_update_local(s, ns, r[:, 3], perms[10:20])
+    oal = og.actor_update(s, ns, r[:, 3], a[:, 3], perms[20])
+    for k in range(6):
+        close(x[k], ox[k], rtol=2e-4, atol=5e-6)
+        close(y[k], oy[k], rtol=2e-4, atol=5e-6)
+        close(g.actor.get_weights()[k], og.actor[k], rtol=2e-4, atol=5e-6)
+    close([xl, yl, al], [oxl, oyl, oal], rtol=1e-4, atol=1e-6)
+    f = Faulty_CAC_agent(*build_models(w[2]), slow_lr=0.002, gamma=0.9)
+    f.perm_source = lambda T: perms[0]
+    before = [m.copy() for m in f.get_critic_weights()]
+    fl = f.actor_update(s, ns, r[:, 2], a[:, 2])
+    of = O.FaultyOracleAgent(w[2][0], w[2][1], w[2][2], 0.002, 0.9, dtype=np.float64)
+    ofl = of.actor_update(s, ns, r[:, 2], a[:, 2], perms[0])
+    close(fl, ofl, rtol=1e-4, atol=1e-6)
+    for k in range(6):
+        close(f.actor.get_weights()[k], of.actor[k], rtol=2e-4, atol=5e-6)
+        assert np.array_equal(f.get_critic_weights()[k], before[k]) and np.array_equal(f.get_TR_weights()[k], w[2][2][k])

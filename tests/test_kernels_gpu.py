@@ -57,7 +57,8 @@ def close(got, want, rtol=1e-4, atol=1e-6):
 
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,H,P", [(4, 0, 661), (4, 1, 640), (6, 2, 1421), (9, 4, 4096), (3, 1, 37),
-                                    (16, 7, 1000), (64, 4, 65536), (64, 1, 65537), (5, 2, 8)])
+                                    (16, 7, 1000), (64, 4, 65536), (64, 1, 65537), (5, 2, 8), (1, 0, 16), (8, 3, 4096),
+                                    (17, 5, 2048), (24, 6, 1024), (64, 2, 4100)])
 def test_clip_mean_matches_oracle(K, n, H, P):
     rs = np.random.RandomState(n * 131 + H)
     v = rs.randn(n, P).astype(np.float32)
@@ -260,7 +261,8 @@ def test_actor_ce_grad_and_keras_adam(K, NA, nrow):
         close(theta, K.nets.pack(w64), rtol=2e-4, atol=2e-6)
 
 
-@pytest.mark.parametrize("NA,nrow,n_in,H", [(5, 5, 4, 0), (5, 5, 4, 1), (16, 10, 6, 2), (5, 5, 1, 0)])
+@pytest.mark.parametrize("NA,nrow,n_in,H", [(5, 5, 4, 0), (5, 5, 4, 1), (16, 10, 6, 2), (5, 5, 1, 0), (16, 10, 16, 7),
+                                            (16, 10, 9, 4), (5, 5, 5, 2)])
 def test_team_estimates_and_projection(K, NA, nrow, n_in, H):
     rs = np.random.RandomState(9 + H)
     B, lr = 1500, 0.01
