@@ -167,13 +167,15 @@ typedef struct {
 int rcmarl_sgd_apply(const rcmarl_sgd_job* jobs_host, int n_jobs, void* stream);
 
 /* K9.  Mini-batch SGD epochs for several networks in lock-step (Keras fit(batch_size=32, epochs=10, shuffle=True),
- * agents/adversarial_CAC_agents.py:133,150,163,239,251), single GPU: for e < epochs, for each batch b of `mb_times`
+ * agents/adversarial_CAC_agents.py:133,150,163,239,251): for e < epochs, for each batch b of `mb_times`
  * time rows: rows = { time_idx_j[e*n_times + b*mb_times + i]*n_envs + env }, gradient (rcmarl_grad, MSE), then
- * theta_j -= lr*2/(rows in batch) * g in place (reduce + apply fused in one kernel).
+ * theta_j -= lr*2/(rows in batch, summed over ranks) * g in place.  Reduction of the CTA partials, the cross-GPU
+ * exchange (when an exchange context is bound, see rcmarl_comm_*) and the SGD apply are ONE kernel; the grad kernel
+ * of the next step starts its prologue under it (programmatic dependent launch).
  * gjobs[j].time_idx must point at that network's [epochs][n_times] permutation table; sjobs[j].dst == src == gjobs[j].w;
  * sjobs[j].loss_out (optional) accumulates sum(e^2)*loss_coef over epoch 0 only (history['loss'][0]).
- * rows->n_rows / time_idx are ignored.  With data parallelism the caller loops over rcmarl_grad / all-reduce /
- * rcmarl_sgd_apply instead. */
+ * rows->n_rows / time_idx are ignored.  Without a bound exchange context a data-parallel caller loops over
+ * rcmarl_grad / all-reduce / rcmarl_sgd_apply instead. */
 int rcmarl_minibatch_sgd(const rcmarl_rows* rows_host, const rcmarl_grad_job* gjobs_host,
                          const rcmarl_sgd_job* sjobs_host, int n_jobs, int epochs, int n_times, int mb_times,
                          float lr, void* ws, int64_t ws_bytes, void* stream);
