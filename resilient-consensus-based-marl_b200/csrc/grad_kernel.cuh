@@ -80,7 +80,11 @@ __host__ __device__ constexpr int stage_floats_per_row(int din, bool is_sa_net) 
 // warps per CTA: as many 64-row tiles as fit next to the staged weights, at most 8
 // Bulk-copy input staging costs 64 x 3*NA x 4 bytes of shared memory per warp.  At n_agents = 5 (3.8 KB per warp) it fits
 // next to 8 tiles; at n_agents = 16 it would cut the CTA from 6 to 4 warps, so those instantiations keep per-lane loads.
+#ifndef RCMARL_NO_TMA
 __host__ __device__ constexpr bool grad_use_tma(int na) { return na <= 5; }
+#else
+__host__ __device__ constexpr bool grad_use_tma(int na) { return false; }
+#endif
 
 template <int DIN, int NOUT, bool SA_NET>
 constexpr int grad_warps_for() {
@@ -123,6 +127,19 @@ struct GradParams {
     int32_t stride;
 };
 
+// 1: the constant columns of the tile rows ([.., 1, 0 pad], zero pads of the deltas) are written once per kernel instead of
+//    once per chunk (3-4 of 22 STS.128 per row).  Measured on B200 together with RCMARL_LRELU_MAX: 10.53 -> 10.30 ms per
+//    full-batch launch, results bit-identical (tools/ab_grad.py).
+#ifndef RCMARL_PAD_HOIST
+#define RCMARL_PAD_HOIST 1
+#endif
+// 1: the CTA signals its programmatic dependents (the reduce kernel of the same mini-batch step, launched with the PDL
+//    attribute) once its row loop is done, so the reduce grid is already queued when the last CTA exits; the reduce kernel
+//    waits for this grid with griddepcontrol.wait.  Measured on B200 (C2): 1192.9 -> 1175.1 ms per update round.
+#ifndef RCMARL_PDL_REDUCE
+#define RCMARL_PDL_REDUCE 1
+#endif
+
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
@@ -150,6 +167,24 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     pdl_wait();                       // everything above overlaps the tail of the previous kernel (PDL)
     stage_weights(sw, job.w, NP);
     __syncthreads();
+    const SmemW W{sw};
+    constexpr bool kPadHoist = RCMARL_PAD_HOIST != 0;
+    if constexpr (kPadHoist) {
+        // the constant columns of this lane's two tile rows ([.., 1, 0 pad] of the activations, zero pad of the deltas)
+        // never change: write them once instead of once per chunk
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float* rowp = wt + (lane + 32 * r) * L::RS;
+#pragma unroll
+            for (int q = 0; q < L::LA1 / 4; ++q)
+                if (4 * q >= DIN) st4(rowp + L::OA1 + 4 * q, 4 * q == DIN ? 1.f : 0.f, 0.f, 0.f, 0.f);
+            st4(rowp + L::OA2 + 20, 1.f, 0.f, 0.f, 0.f);
+            if constexpr (L::L3T) st4(rowp + L::OA3 + 20, 1.f, 0.f, 0.f, 0.f);
+            st4(rowp + L::OD1 + 20, 0.f, 0.f, 0.f, 0.f);
+            st4(rowp + L::OD2 + 20, 0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+    }
 
     // Input staging by the TMA engine: the 64 rows of a chunk are one contiguous, 16-byte aligned span of sa / ns whenever
     // the chunk is full and (contiguous row mode, or gathered mode with n_envs % 64 == 0); lane 0 issues one 1-D bulk copy
@@ -226,12 +261,13 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
                         bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
                     }
                 }
-                dense20_rows<DIN, R>(sw, sw + off_b1(DIN), x, h1);
+                dense20_rows<DIN, R>(W, 0, off_b1(DIN), x, h1);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     float* a1 = wt + (lane + 32 * r) * L::RS + L::OA1;
 #pragma unroll
                     for (int q = 0; q < L::LA1 / 4; ++q) {
+                        if (kPadHoist && 4 * q >= DIN) continue;
                         float v[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -242,30 +278,29 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
                     }
                 }
             }
-            dense20_rows<HID, R>(sw + off_W2(DIN), sw + off_b2(DIN), h1, h2);
+            dense20_rows<HID, R>(W, off_W2(DIN), off_b2(DIN), h1, h2);
             float d2[R][HID];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float* rowp = wt + (lane + 32 * r) * L::RS;
 #pragma unroll
                 for (int q = 0; q < 5; ++q) st4(rowp + L::OA2 + 4 * q, h1[r][4 * q], h1[r][4 * q + 1], h1[r][4 * q + 2], h1[r][4 * q + 3]);
-                st4(rowp + L::OA2 + 20, 1.f, 0.f, 0.f, 0.f);
+                if constexpr (!kPadHoist) st4(rowp + L::OA2 + 20, 1.f, 0.f, 0.f, 0.f);
                 const float tgt = live[r] ? __ldg(job.target + row[r] * job.target_stride) : 0.f;
-                const float* W3 = sw + off_W3(DIN);
                 if constexpr (NOUT == 1) {
                     // Keras MSE (Appendix A.2): dLoss/dout = 2 (out - y) / B; the 2/B is applied by the caller
-                    const float e = live[r] ? head1<DIN>(sw, h2[r]) - tgt : 0.f;
+                    const float e = live[r] ? head1_w<DIN>(W, h2[r]) - tgt : 0.f;
                     loss = fmaf(e, e, loss);
 #pragma unroll
                     for (int j = 0; j < HID; ++j) {
                         g3[j] = fmaf(h2[r][j], e, g3[j]);
-                        d2[r][j] = W3[j] * e * lrelu_grad_from_out(h2[r][j]);
+                        d2[r][j] = W.s(off_W3(DIN) + j) * e * lrelu_grad_from_out(h2[r][j]);
                     }
                     g3[HID] += e;
                 } else {
                     // weighted sparse categorical cross-entropy on the logits (Appendix A.5)
                     float p[NACT], mx, lse, g[NACT];
-                    head5<DIN>(sw, h2[r], p);
+                    head5_w<DIN>(W, h2[r], p);
                     const int a = (int)__ldg(Rw.sa + row[r] * (3 * NA) + 3 * job.action_agent + 2);
                     float la = 0.f;
 #pragma unroll
@@ -276,23 +311,22 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
                     for (int o = 0; o < NACT; ++o) g[o] = (p[o] - (o == a ? 1.f : 0.f)) * tgt;
 #pragma unroll
                     for (int q = 0; q < 5; ++q) st4(rowp + L::OA3 + 4 * q, h2[r][4 * q], h2[r][4 * q + 1], h2[r][4 * q + 2], h2[r][4 * q + 3]);
-                    st4(rowp + L::OA3 + 20, 1.f, 0.f, 0.f, 0.f);
+                    if constexpr (!kPadHoist) st4(rowp + L::OA3 + 20, 1.f, 0.f, 0.f, 0.f);
                     st4(rowp + L::OD3, g[0], g[1], g[2], g[3]);
                     st4(rowp + L::OD3 + 4, g[4], 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < HID; ++j) {
                         float s = 0.f;
 #pragma unroll
-                        for (int o = 0; o < NACT; ++o) s = fmaf(W3[j * NACT + o], g[o], s);
+                        for (int o = 0; o < NACT; ++o) s = fmaf(W.s(off_W3(DIN) + j * NACT + o), g[o], s);
                         d2[r][j] = s * lrelu_grad_from_out(h2[r][j]);
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < 5; ++q) st4(rowp + L::OD2 + 4 * q, d2[r][4 * q], d2[r][4 * q + 1], d2[r][4 * q + 2], d2[r][4 * q + 3]);
-                st4(rowp + L::OD2 + 20, 0.f, 0.f, 0.f, 0.f);
+                if constexpr (!kPadHoist) st4(rowp + L::OD2 + 20, 0.f, 0.f, 0.f, 0.f);
             }
             // delta1[i] = (W2[i][:] . delta2) * lrelu'(z1[i]) for both rows; each W2 quad feeds 8 FFMA
-            const float* W2 = sw + off_W2(DIN);
             f2 d2p[R][HID / 2];
 #pragma unroll
             for (int r = 0; r < R; ++r)
@@ -304,13 +338,12 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const int i = 4 * q + ii;
-                    const float4* w = reinterpret_cast<const float4*>(W2 + i * HID);
                     f2 s[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) s[r] = pack2(0.f, 0.f);
 #pragma unroll
                     for (int qq = 0; qq < 5; ++qq) {
-                        const float4 v = w[qq];
+                        const float4 v = W.q(off_W2(DIN) + i * HID + 4 * qq);
                         const f2 w0 = pack2(v.x, v.y), w1 = pack2(v.z, v.w);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
@@ -330,7 +363,8 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
                     st4(wt + (lane + 32 * r) * L::RS + L::OD1 + 4 * q, d1[r][0], d1[r][1], d1[r][2], d1[r][3]);
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) st4(wt + (lane + 32 * r) * L::RS + L::OD1 + 20, 0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < R; ++r)
+                if constexpr (!kPadHoist) st4(wt + (lane + 32 * r) * L::RS + L::OD1 + 20, 0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
         // ---------------- phase 2: 8x8 register tile per lane, NG rows per step ----------------
@@ -358,6 +392,9 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     }
 
     // ---------------- CTA reduction (fixed order => bitwise reproducible) ----------------
+#if RCMARL_PDL_REDUCE
+    pdl_launch_dependents();
+#endif
     __syncthreads();
     float* red = tiles;                               // [GRAD_WARPS][32][64]
     {

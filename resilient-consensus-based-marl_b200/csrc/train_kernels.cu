@@ -158,6 +158,9 @@ struct ReduceSgdParams {
 __global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__ ReduceSgdParams P) {
     __shared__ float sh[256];
     pdl_launch_dependents();     // the next grad kernel may start its prologue; it waits (pdl_wait) before reading
+#if RCMARL_PDL_REDUCE
+    pdl_wait();                  // launched as a programmatic dependent of the grad kernel: its partials must be complete
+#endif
     const rcmarl_sgd_job& job = P.jobs[blockIdx.y];
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const bool valid = i <= job.n;
@@ -185,6 +188,9 @@ struct ReduceCommParams {
 __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant__ ReduceCommParams P) {
     __shared__ float sh[256];
     pdl_launch_dependents();     // the next grad kernel may start its prologue; it waits (pdl_wait) before reading
+#if RCMARL_PDL_REDUCE
+    pdl_wait();
+#endif
     const int j = blockIdx.y;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const int nj = P.n[j];
@@ -470,6 +476,28 @@ static int launch_team(const TeamParams& P, int gy, cudaStream_t st) {
     return 0;
 }
 
+// launch of the fused reduce kernels of the mini-batch loop; with RCMARL_PDL_REDUCE as a programmatic dependent of the
+// grad kernel before it (the kernel itself waits for that grid with griddepcontrol.wait)
+template <typename K, typename PT>
+static int launch_reduce(K kernel, const PT& params, dim3 grid, cudaStream_t st) {
+#if RCMARL_PDL_REDUCE
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cfg.attrs = &pdl;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
+#else
+    kernel<<<grid, 256, 0, st>>>(params);
+#endif
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int grid_y_for(int64_t work_items, int n_jobs, int ctas_per_sm) {
     // one resident wave at most: gridDim.x * gridDim.y <= SMs * CTAs-per-SM (a partial second wave would
     // double the kernel time of these persistent, equal-work CTAs)
@@ -615,11 +643,10 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
                     C.sgd[j] = Q.jobs[j];
                     C.sgd[j].coef = lr * 2.0f / ((float)n_rows * (float)C.comm.world);   // global batch
                 }
-                reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
+                if (launch_reduce(reduce_comm_kernel, C, dim3((maxn + 31) / 32, n_jobs), st)) return RCMARL_ERR_CUDA;
             } else {
-                reduce_sgd_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(Q);
+                if (launch_reduce(reduce_sgd_kernel, Q, dim3((maxn + 31) / 32, n_jobs), st)) return RCMARL_ERR_CUDA;
             }
-            RC_CUDA(cudaGetLastError());
         }
     }
     return RCMARL_OK;
