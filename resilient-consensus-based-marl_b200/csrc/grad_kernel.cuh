@@ -101,6 +101,15 @@ constexpr int grad_warps() {
     return a < b ? a : b;
 }
 
+// Relative cost of one buffer row for a job (FMA issue slots per lane-row): phase 1 (forward, output layer, backward-data)
+// plus phase 2 (the NT 8x8 tiles are spread over NG row groups, so a 64-row chunk takes 64 / NG tile steps of 64 FMA).
+__host__ __device__ constexpr int grad_row_cost(int din, int nout) {
+    const int la1 = round8(din + 1);
+    const int nt = (la1 / 8) * 3 + 9 + (nout > 1 ? 3 : 0);
+    const int ng = 32 / nt;
+    return din * HID + 2 * HID * HID + 2 * HID * nout + 2048 / ng;
+}
+
 // ---- 1-D bulk copy (TMA engine, SASS UBLKCP) of the next chunk's input rows into a warp-private staging buffer ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -122,9 +131,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 struct GradParams {
     rcmarl_rows rows;
     rcmarl_grad_job jobs[RCMARL_MAX_JOBS];
-    float* partial;   // [gridDim.y][n_jobs][stride]
+    float* partial;   // [CTA][stride]: one slot per CTA of the 1-D grid
     int32_t n_jobs;
     int32_t stride;
+    // job j owns the CTAs [cta_first[j], cta_first[j + 1]) of the 1-D grid (train_kernels.cu, plan_grad_grid)
+    int16_t cta_first[RCMARL_MAX_JOBS + 1];
 };
 
 // 1: the constant columns of the tile rows ([.., 1, 0 pad], zero pads of the deltas) are written once per kernel instead of
@@ -144,8 +155,9 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
+// y / gy: index of this CTA among the gy CTAs of its job
 template <int NA, int DIN, int NOUT, int GRAD_WARPS>
-__device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad_job& job, float* smem) {
+__device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad_job& job, float* smem, int y, int gy) {
     using L = TileLayout<DIN, NOUT>;
     constexpr int NP = param_count(DIN, NOUT);
     constexpr int R = 2;
@@ -200,9 +212,9 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     };
     uint32_t phase = 0;
     bool staged = false;
-    const int64_t cstep = (int64_t)gridDim.y * GRAD_WARPS;
+    const int64_t cstep = (int64_t)gy * GRAD_WARPS;
     {
-        const int64_t c0 = (int64_t)blockIdx.y * GRAD_WARPS + warp;
+        const int64_t c0 = (int64_t)y * GRAD_WARPS + warp;
         const float* src = nullptr;
         if (c0 * L::ROWS < Rw.n_rows) staged = stage_src(c0, src);
         if (staged && lane == 0) bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
@@ -223,7 +235,7 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     float loss = 0.f;
 
     const int64_t nchunks = (Rw.n_rows + L::ROWS - 1) / L::ROWS;
-    for (int64_t c = (int64_t)blockIdx.y * GRAD_WARPS + warp; c < nchunks; c += cstep) {
+    for (int64_t c = (int64_t)y * GRAD_WARPS + warp; c < nchunks; c += cstep) {
         // ---------------- phase 1: two rows per lane (lane, lane + 32 of the chunk) ----------------
         {
             bool live[R];
@@ -418,7 +430,7 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
         }
     }
     __syncthreads();
-    float* out = P.partial + ((int64_t)blockIdx.y * P.n_jobs + blockIdx.x) * P.stride;
+    float* out = P.partial + (int64_t)blockIdx.x * P.stride;
     for (int q = threadIdx.x; q < L::NT * 64; q += blockDim.x) {
         const int t = q >> 6, e = q & 63;
         const int idx = L::tile_param(t, e >> 3, e & 7);
@@ -448,13 +460,16 @@ template <int NA, int LOSS>
 __global__ void __launch_bounds__(32 * grad_warps<NA, LOSS>(), 1) grad_kernel(const __grid_constant__ GradParams P) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NW = grad_warps<NA, LOSS>();
-    const rcmarl_grad_job& job = P.jobs[blockIdx.x];
+    int j = 0;
+    while (j + 1 < P.n_jobs && (int)blockIdx.x >= P.cta_first[j + 1]) ++j;
+    const rcmarl_grad_job& job = P.jobs[j];
+    const int y = (int)blockIdx.x - P.cta_first[j], gy = P.cta_first[j + 1] - P.cta_first[j];
     if (LOSS == RCMARL_LOSS_CE) {
-        grad_body<NA, 2 * NA, NACT, NW>(P, job, smem);
+        grad_body<NA, 2 * NA, NACT, NW>(P, job, smem, y, gy);
     } else if (job.kind == RCMARL_IN_SA) {
-        grad_body<NA, 3 * NA, 1, NW>(P, job, smem);
+        grad_body<NA, 3 * NA, 1, NW>(P, job, smem, y, gy);
     } else {
-        grad_body<NA, 2 * NA, 1, NW>(P, job, smem);
+        grad_body<NA, 2 * NA, 1, NW>(P, job, smem, y, gy);
     }
 }
 

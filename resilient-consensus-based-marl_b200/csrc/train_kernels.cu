@@ -12,6 +12,7 @@
 //
 // Reference semantics: agents/resilient_CAC_agents.py, agents/adversarial_CAC_agents.py,
 // training/train_agents.py:86-163 (cited per entry point in include/rcmarl.h).
+#include <stdlib.h>
 #include "common.cuh"
 #include "grad_kernel.cuh"
 #include "comm.cuh"
@@ -113,15 +114,24 @@ __global__ void __launch_bounds__(256) values_kernel(const __grid_constant__ Val
     }
 }
 
-// Deterministic sum over the gy CTA partials of one parameter, parallel over the 8 warps of a 256-thread block:
+// Where the CTA partials of job j live: slots first[j] + y * step, y = 0 .. count[j] - 1, each `stride` floats
+// (grad_kernel: consecutive slots of the 1-D grid; team_kernel: [y][job] interleaved).
+struct PartialSlots {
+    int32_t first[RCMARL_MAX_JOBS];
+    int32_t count[RCMARL_MAX_JOBS];
+    int32_t step, stride;
+};
+
+// Deterministic sum over the CTA partials of one parameter, parallel over the 8 warps of a 256-thread block:
 // block b of job j owns parameters [32 b, 32 b + 32); warp w adds y = w, w + 8, ... (coalesced 128-byte rows), the
 // eight warp sums are combined in warp order.  Returns the total in the threads of warp 0 (others return 0).
-__device__ __forceinline__ float block_partial_sum(const float* __restrict__ partial, int n_jobs, int stride, int gy,
-                                                   int j, int i, bool valid, float* sh /* [8][32] */) {
+__device__ __forceinline__ float block_partial_sum(const float* __restrict__ partial, const PartialSlots& S, int j, int i,
+                                                   bool valid, float* sh /* [8][32] */) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = S.first[j], count = S.count[j];
     float s = 0.f;
     if (valid)
-        for (int y = warp; y < gy; y += 8) s += partial[((int64_t)y * n_jobs + j) * stride + i];
+        for (int y = warp; y < count; y += 8) s += partial[((int64_t)first + (int64_t)y * S.step) * S.stride + i];
     sh[warp * 32 + lane] = s;
     __syncthreads();
     float tot = 0.f;
@@ -137,7 +147,7 @@ struct ReduceParams {
     const float* partial;
     float* sums[RCMARL_MAX_JOBS];
     int32_t n[RCMARL_MAX_JOBS];
-    int32_t n_jobs, stride, gy;
+    PartialSlots slots;
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ ReduceParams P) {
     __shared__ float sh[256];
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ Red
     const int j = blockIdx.y;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const bool valid = i < P.n[j];
-    const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, j, i, valid, sh);
+    const float s = block_partial_sum(P.partial, P.slots, j, i, valid, sh);
     if (threadIdx.x < 32 && valid) P.sums[j][i] = s;
 }
 
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ Red
 struct ReduceSgdParams {
     const float* partial;
     rcmarl_sgd_job jobs[RCMARL_MAX_JOBS];
-    int32_t n_jobs, stride, gy;
+    PartialSlots slots;
 };
 __global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__ ReduceSgdParams P) {
     __shared__ float sh[256];
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(256) reduce_sgd_kernel(const __grid_constant__
     const rcmarl_sgd_job& job = P.jobs[blockIdx.y];
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const bool valid = i <= job.n;
-    const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, blockIdx.y, i, valid, sh);
+    const float s = block_partial_sum(P.partial, P.slots, blockIdx.y, i, valid, sh);
     if (threadIdx.x >= 32 || !valid) return;
     if (i < job.n) {
         const float v = job.src[i];
@@ -182,7 +192,8 @@ struct ReduceCommParams {
     float* sums[RCMARL_MAX_JOBS];
     int32_t n[RCMARL_MAX_JOBS];
     rcmarl_sgd_job sgd[RCMARL_MAX_JOBS];
-    int32_t n_jobs, stride, gy, fuse_sgd;
+    PartialSlots slots;
+    int32_t out_stride, fuse_sgd;     // out_stride: distance between the jobs' blocks in the exchange buffer
     CommDev comm;
 };
 __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant__ ReduceCommParams P) {
@@ -195,8 +206,8 @@ __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant_
     const int i = blockIdx.x * 32 + (threadIdx.x & 31);
     const int nj = P.n[j];
     const bool valid = i < nj;
-    const int64_t off = (int64_t)j * P.stride + i;
-    const float s = block_partial_sum(P.partial, P.n_jobs, P.stride, P.gy, j, i, valid, sh);
+    const int64_t off = (int64_t)j * P.out_stride + i;
+    const float s = block_partial_sum(P.partial, P.slots, j, i, valid, sh);
     if (threadIdx.x < 32 && valid) comm_push(P.comm, off, s);
     comm_publish_and_wait(P.comm, gridDim.x * gridDim.y);
     if (threadIdx.x < 32 && valid) {
@@ -425,7 +436,7 @@ static int launch_values(const ValuesParams& P, int n_jobs, cudaStream_t st) {
 }
 
 template <int NA>
-static int launch_grad(GradParams& P, int loss_mode, int gy, cudaStream_t st) {
+static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st) {
     constexpr int NWM = grad_warps<NA, RCMARL_LOSS_MSE>(), NWC = grad_warps<NA, RCMARL_LOSS_CE>();
     constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<NA, 3 * NA, 1, NWM>() > grad_smem_floats<NA, 2 * NA, 1, NWM>()
                                                      ? grad_smem_floats<NA, 3 * NA, 1, NWM>() : grad_smem_floats<NA, 2 * NA, 1, NWM>());
@@ -436,7 +447,7 @@ static int launch_grad(GradParams& P, int loss_mode, int gy, cudaStream_t st) {
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl.val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(P.n_jobs, gy);
+    cfg.gridDim = dim3(n_ctas);
     cfg.stream = st;
     cfg.attrs = &pdl;
     cfg.numAttrs = 1;
@@ -507,6 +518,68 @@ static int grid_y_for(int64_t work_items, int n_jobs, int ctas_per_sm) {
     return (int)(gy < 1 ? 1 : gy);
 }
 
+// Shares of the one-wave, 1-D grid of grad_kernel: job j owns the CTAs [cta_first[j], cta_first[j + 1]).
+// Default: equal shares, floor(SMs / n_jobs) CTAs per job (all jobs then sweep the rows in lock-step, which keeps the
+// buffer rows they share in L2).  RCMARL_BALANCED_GRID=1 in the environment sizes the shares by cost instead: a job's
+// cost per row depends on its network (grad_row_cost) and a CTA works in rounds of `gw` 64-row chunks, so with 148 SMs
+// 4 team-reward + 4 critic jobs get 19 + 18 CTAs each instead of 18 + 18, and the 3 chains of a malicious agent
+// 48 / 52 / 48 instead of 49 each (the team-reward job then needs 5 rounds instead of 6); greedy: the job that currently
+// finishes last gets the next CTA.  Measured on B200 (profiles/r01_late_variants.md, run 3): -1.2 % / -2.2 % on isolated
+// full-batch / mini-batch launches but +1.5 % on the C2 update round, so it stays opt-in until that is understood.
+#ifndef RCMARL_BALANCED_GRID_DEFAULT
+#define RCMARL_BALANCED_GRID_DEFAULT 0
+#endif
+static bool balanced_grid_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RCMARL_BALANCED_GRID");
+        v = e ? (e[0] != '0') : RCMARL_BALANCED_GRID_DEFAULT;
+    }
+    return v != 0;
+}
+
+static int plan_grad_grid(GradParams& P, PartialSlots& S, const int* cost, int64_t nchunks, int gw) {
+    const int n = P.n_jobs, sms = sm_count_cached();
+    int64_t units = (nchunks + gw - 1) / gw;
+    if (units < 1) units = 1;
+    int g[RCMARL_MAX_JOBS];
+    if (!balanced_grid_enabled() || n == 1 || n > sms) {
+        const int gy = grid_y_for(units, n, 1);
+        for (int j = 0; j < n; ++j) g[j] = gy;
+    } else {
+        int used = n;
+        for (int j = 0; j < n; ++j) g[j] = 1;
+        while (used < sms) {
+            int best = -1;
+            int64_t best_t = -1;
+            for (int j = 0; j < n; ++j) {
+                if (g[j] >= units) continue;
+                const int64_t per_round = (int64_t)g[j] * gw;
+                const int64_t t = ((nchunks + per_round - 1) / per_round) * cost[j];
+                if (t > best_t || (t == best_t && g[j] < g[best])) { best_t = t; best = j; }
+            }
+            if (best < 0) break;
+            ++g[best];
+            ++used;
+        }
+    }
+    int first = 0;
+    for (int j = 0; j < n; ++j) {
+        P.cta_first[j] = (int16_t)first;
+        S.first[j] = first;
+        S.count[j] = g[j];
+        first += g[j];
+    }
+    P.cta_first[n] = (int16_t)first;
+    S.step = 1;
+    return first;
+}
+
+static int grad_job_cost(int na, int kind, int loss_mode) {
+    if (loss_mode == RCMARL_LOSS_CE) return grad_row_cost(2 * na, NACT);
+    return grad_row_cost(kind == RCMARL_IN_SA ? 3 * na : 2 * na, 1);
+}
+
 }  // namespace rcmarl
 
 using namespace rcmarl;
@@ -547,6 +620,7 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
     ReduceParams Q;
     P.rows = *rows;
     int maxn = 0;
+    int cost[RCMARL_MAX_JOBS];
     for (int j = 0; j < n_jobs; ++j) {
         const rcmarl_grad_job& q = jobs[j];
         if (!q.w || !q.target || !q.sums || q.kind < 0 || q.kind > 2 || q.target_stride < 1) return RCMARL_ERR_ARG;
@@ -558,26 +632,25 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
                                                    : param_count(q.kind == RCMARL_IN_SA ? 3 * NA : 2 * NA, 1);
         Q.sums[j] = q.sums;
         Q.n[j] = n + 1;
+        cost[j] = grad_job_cost(NA, q.kind, loss_mode);
         if (n + 1 > maxn) maxn = n + 1;
     }
     const int64_t nchunks = (rows->n_rows + 63) / 64;
     const int cpc = NA == 5 ? grad_chunks_per_cta<5>(loss_mode) : grad_chunks_per_cta<16>(loss_mode);
-    const int gy = grid_y_for((nchunks + cpc - 1) / cpc, n_jobs, 1);
-    if ((int64_t)gy * n_jobs * maxn * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
     P.partial = (float*)ws;
     P.n_jobs = n_jobs;
     P.stride = maxn;
+    Q.slots.stride = maxn;
+    const int n_ctas = plan_grad_grid(P, Q.slots, cost, nchunks, cpc);
+    if ((int64_t)n_ctas * maxn * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    int e = NA == 5 ? launch_grad<5>(P, loss_mode, gy, st) : launch_grad<16>(P, loss_mode, gy, st);
+    int e = NA == 5 ? launch_grad<5>(P, loss_mode, n_ctas, st) : launch_grad<16>(P, loss_mode, n_ctas, st);
     if (e) return e;
     Q.partial = (const float*)ws;
-    Q.n_jobs = n_jobs;
-    Q.stride = maxn;
-    Q.gy = gy;
     if (comm_bound()) {
         ReduceCommParams C;
         if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
-        C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = maxn; C.gy = gy; C.fuse_sgd = 0;
+        C.partial = Q.partial; C.slots = Q.slots; C.out_stride = maxn; C.fuse_sgd = 0;
         for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
         reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
     } else {
@@ -598,6 +671,7 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
     ReduceSgdParams Q;
     P.rows = *rows;
     int maxn = 0;
+    int cost[RCMARL_MAX_JOBS];
     for (int j = 0; j < n_jobs; ++j) {
         const rcmarl_grad_job& q = gjobs[j];
         if (!q.w || !q.target || !q.time_idx || q.kind < 0 || q.kind > 2 || q.target_stride < 1) return RCMARL_ERR_ARG;
@@ -606,14 +680,15 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
         if (sjobs[j].n != n) return RCMARL_ERR_ARG;
         P.jobs[j] = q;
         Q.jobs[j] = sjobs[j];
+        cost[j] = grad_job_cost(NA, q.kind, RCMARL_LOSS_MSE);
         if (n + 1 > maxn) maxn = n + 1;
     }
     P.partial = (float*)ws;
     P.n_jobs = n_jobs;
     P.stride = maxn;
     Q.partial = (const float*)ws;
-    Q.n_jobs = n_jobs;
-    Q.stride = maxn;
+    Q.slots.stride = maxn;
+    int n_ctas = 0, planned_cnt = -1;
     cudaStream_t st = (cudaStream_t)stream;
     const int cpc = NA == 5 ? grad_chunks_per_cta<5>(RCMARL_LOSS_MSE) : grad_chunks_per_cta<16>(RCMARL_LOSS_MSE);
     for (int e = 0; e < epochs; ++e) {
@@ -621,22 +696,23 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
             const int cnt = n_times - b < mb_times ? n_times - b : mb_times;
             const int64_t n_rows = (int64_t)cnt * rows->n_envs;
             P.rows.n_rows = n_rows;
-            const int64_t nchunks = (n_rows + 63) / 64;
-            const int gy = grid_y_for((nchunks + cpc - 1) / cpc, n_jobs, 1);
-            if ((int64_t)gy * n_jobs * maxn * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
+            if (cnt != planned_cnt) {                        // the grid only depends on the mini-batch size
+                n_ctas = plan_grad_grid(P, Q.slots, cost, (n_rows + 63) / 64, cpc);
+                if ((int64_t)n_ctas * maxn * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
+                planned_cnt = cnt;
+            }
             for (int j = 0; j < n_jobs; ++j) {
                 P.jobs[j].time_idx = gjobs[j].time_idx + (int64_t)e * n_times + b;
                 Q.jobs[j].coef = lr * 2.0f / (float)n_rows;
                 if (e > 0) Q.jobs[j].loss_out = nullptr;
             }
             P.rows.time_idx = P.jobs[0].time_idx;
-            int err = NA == 5 ? launch_grad<5>(P, RCMARL_LOSS_MSE, gy, st) : launch_grad<16>(P, RCMARL_LOSS_MSE, gy, st);
+            int err = NA == 5 ? launch_grad<5>(P, RCMARL_LOSS_MSE, n_ctas, st) : launch_grad<16>(P, RCMARL_LOSS_MSE, n_ctas, st);
             if (err) return err;
-            Q.gy = gy;
             if (comm_bound()) {
                 ReduceCommParams C;
                 if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
-                C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = maxn; C.gy = gy; C.fuse_sgd = 1;
+                C.partial = Q.partial; C.slots = Q.slots; C.out_stride = maxn; C.fuse_sgd = 1;
                 for (int j = 0; j < n_jobs; ++j) {
                     C.sums[j] = nullptr;
                     C.n[j] = Q.jobs[j].n + 1;
@@ -685,13 +761,13 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
     if (e) return e;
     if (any_sums) {
         Q.partial = (const float*)ws;
-        Q.n_jobs = n_jobs;
-        Q.stride = TEAM_N;
-        Q.gy = gy;
+        Q.slots.step = n_jobs;                    // team_kernel writes its partials [y][job] interleaved
+        Q.slots.stride = TEAM_N;
+        for (int j = 0; j < n_jobs; ++j) { Q.slots.first[j] = j; Q.slots.count[j] = gy; }
         if (comm_bound()) {
             ReduceCommParams C;
             if (!comm_next(&C.comm, (int64_t)n_jobs * TEAM_N)) return RCMARL_ERR_ARG;
-            C.partial = Q.partial; C.n_jobs = n_jobs; C.stride = TEAM_N; C.gy = gy; C.fuse_sgd = 0;
+            C.partial = Q.partial; C.slots = Q.slots; C.out_stride = TEAM_N; C.fuse_sgd = 0;
             for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
             reduce_comm_kernel<<<dim3((TEAM_N + 31) / 32, n_jobs), 256, 0, st>>>(C);
         } else {
