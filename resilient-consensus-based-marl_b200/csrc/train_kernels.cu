@@ -719,7 +719,9 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
                     C.sgd[j] = Q.jobs[j];
                     C.sgd[j].coef = lr * 2.0f / ((float)n_rows * (float)C.comm.world);   // global batch
                 }
-                if (launch_reduce(reduce_comm_kernel, C, dim3((maxn + 31) / 32, n_jobs), st)) return RCMARL_ERR_CUDA;
+                // plain launch: the PDL-launched form was only measured on one GPU (profiles/r01_late_variants.md)
+                reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
+                RC_CUDA(cudaGetLastError());
             } else {
                 if (launch_reduce(reduce_sgd_kernel, Q, dim3((maxn + 31) / 32, n_jobs), st)) return RCMARL_ERR_CUDA;
             }
