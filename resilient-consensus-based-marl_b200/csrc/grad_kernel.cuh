@@ -147,6 +147,11 @@ struct GradParams {
 // 1: the CTA signals its programmatic dependents (the reduce kernel of the same mini-batch step, launched with the PDL
 //    attribute) once its row loop is done, so the reduce grid is already queued when the last CTA exits; the reduce kernel
 //    waits for this grid with griddepcontrol.wait.  Measured on B200 (C2): 1192.9 -> 1175.1 ms per update round.
+// 1: warp-major assignment of 64-row chunks to (CTA, warp), see grad_body (not yet measured on the GPU: added after the
+//    round-1 GPU budget was spent; 0 restores the measured CTA-major order)
+#ifndef RCMARL_CHUNK_WARP_MAJOR
+#define RCMARL_CHUNK_WARP_MAJOR 1
+#endif
 #ifndef RCMARL_PDL_REDUCE
 #define RCMARL_PDL_REDUCE 1
 #endif
@@ -212,9 +217,19 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     };
     uint32_t phase = 0;
     bool staged = false;
+    // Chunk c of the job goes to (CTA y, warp w) with c = k * cstep + w * gy + y (RCMARL_CHUNK_WARP_MAJOR, default) or
+    // c = k * cstep + y * GRAD_WARPS + w.  Both cover every chunk exactly once; they differ in who runs the last, partial
+    // round: warp-major leaves one or two busy warps on every SM (on different schedulers, so they run faster alone),
+    // CTA-major leaves a few SMs with all warps busy and the others idle -- at the C2 mini-batch shape (2048 chunks per
+    // job on 49 x 8 warps = 5.22 rounds) the whole launch then waits for a full sixth round on 11 SMs.
     const int64_t cstep = (int64_t)gy * GRAD_WARPS;
+#if RCMARL_CHUNK_WARP_MAJOR
+    const int64_t cfirst = (int64_t)warp * gy + y;
+#else
+    const int64_t cfirst = (int64_t)y * GRAD_WARPS + warp;
+#endif
     {
-        const int64_t c0 = (int64_t)y * GRAD_WARPS + warp;
+        const int64_t c0 = cfirst;
         const float* src = nullptr;
         if (c0 * L::ROWS < Rw.n_rows) staged = stage_src(c0, src);
         if (staged && lane == 0) bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
@@ -235,7 +250,7 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
     float loss = 0.f;
 
     const int64_t nchunks = (Rw.n_rows + L::ROWS - 1) / L::ROWS;
-    for (int64_t c = (int64_t)y * GRAD_WARPS + warp; c < nchunks; c += cstep) {
+    for (int64_t c = cfirst; c < nchunks; c += cstep) {
         // ---------------- phase 1: two rows per lane (lane, lane + 32 of the chunk) ----------------
         {
             bool live[R];
