@@ -1,10 +1,10 @@
 // train_kernels.cu -- update-round kernels of the RPBCAC hot path (sm_100a, fp32 FFMA).
 //
 //   values_kernel   K1/K3  batched forward values / TD targets / TD errors / actor probabilities
-//   grad_kernel     K2/K7/K9  fused forward + backward of the 20-wide MLPs over a row set:
-//                   phase 1: one buffer row per lane, weights broadcast from shared memory;
+//   grad_kernel     K2/K7/K9  fused forward + backward of the 20-wide MLPs over a row set (grad_kernel.cuh):
+//                   phase 1: two buffer rows per lane, weights broadcast from shared memory;
 //                   phase 2: the per-row activation / delta vectors are staged in a warp-private
-//                            shared-memory tile and every lane owns 4x4 blocks of the weight-gradient
+//                            shared-memory tile and every lane owns one 8x8 tile of the weight-gradient
 //                            outer products, accumulated in registers across ALL rows of the CTA;
 //                   deterministic two-level reduction (CTA partials -> reduce_kernel).
 //   team_kernel     K5+K6  neighbour-head estimates, clipped mean, projection numerators
@@ -15,6 +15,20 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "grad_kernel.cuh"
+// RCMARL_GRAD_V4=1 (make variant_v5): the experimental TMEM-parked exact-fit-tile kernel replaces grad_kernel
+#ifndef RCMARL_GRAD_V4
+#define RCMARL_GRAD_V4 0
+#endif
+#if RCMARL_GRAD_V4
+#include "grad_kernel_v4.cuh"
+#define RC_GRAD_KERNEL grad_kernel_v4
+#define RC_GRAD_WARPS grad4_warps
+#define RC_GRAD_SMEM grad4_smem_floats
+#else
+#define RC_GRAD_KERNEL grad_kernel
+#define RC_GRAD_WARPS grad_warps
+#define RC_GRAD_SMEM grad_smem_floats
+#endif
 #include "comm.cuh"
 
 namespace rcmarl {
@@ -437,10 +451,10 @@ static int launch_values(const ValuesParams& P, int n_jobs, cudaStream_t st) {
 
 template <int NA>
 static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st) {
-    constexpr int NWM = grad_warps<NA, RCMARL_LOSS_MSE>(), NWC = grad_warps<NA, RCMARL_LOSS_CE>();
-    constexpr size_t smem_mse = sizeof(float) * (grad_smem_floats<NA, 3 * NA, 1, NWM>() > grad_smem_floats<NA, 2 * NA, 1, NWM>()
-                                                     ? grad_smem_floats<NA, 3 * NA, 1, NWM>() : grad_smem_floats<NA, 2 * NA, 1, NWM>());
-    constexpr size_t smem_ce = sizeof(float) * grad_smem_floats<NA, 2 * NA, NACT, NWC>();
+    constexpr int NWM = RC_GRAD_WARPS<NA, RCMARL_LOSS_MSE>(), NWC = RC_GRAD_WARPS<NA, RCMARL_LOSS_CE>();
+    constexpr size_t smem_mse = sizeof(float) * (RC_GRAD_SMEM<NA, 3 * NA, 1, NWM>() > RC_GRAD_SMEM<NA, 2 * NA, 1, NWM>()
+                                                     ? RC_GRAD_SMEM<NA, 3 * NA, 1, NWM>() : RC_GRAD_SMEM<NA, 2 * NA, 1, NWM>());
+    constexpr size_t smem_ce = sizeof(float) * RC_GRAD_SMEM<NA, 2 * NA, NACT, NWC>();
     static_assert(smem_mse <= 227 * 1024 && smem_ce <= 227 * 1024, "grad kernel exceeds the 227 KB shared-memory limit");
     static bool attr_ce = false, attr_mse = false;     // opt-in to > 48 KB dynamic shared memory once per process
     cudaLaunchAttribute pdl;
@@ -453,20 +467,20 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
     cfg.numAttrs = 1;
     if (loss_mode == RCMARL_LOSS_CE) {
         if (!attr_ce) {
-            if (set_smem(grad_kernel<NA, RCMARL_LOSS_CE>, smem_ce)) return RCMARL_ERR_CUDA;
+            if (set_smem(RC_GRAD_KERNEL<NA, RCMARL_LOSS_CE>, smem_ce)) return RCMARL_ERR_CUDA;
             attr_ce = true;
         }
         cfg.blockDim = dim3(32 * NWC);
         cfg.dynamicSmemBytes = smem_ce;
-        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel<NA, RCMARL_LOSS_CE>, P));
+        RC_CUDA(cudaLaunchKernelEx(&cfg, RC_GRAD_KERNEL<NA, RCMARL_LOSS_CE>, P));
     } else {
         if (!attr_mse) {
-            if (set_smem(grad_kernel<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
+            if (set_smem(RC_GRAD_KERNEL<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
             attr_mse = true;
         }
         cfg.blockDim = dim3(32 * NWM);
         cfg.dynamicSmemBytes = smem_mse;
-        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel<NA, RCMARL_LOSS_MSE>, P));
+        RC_CUDA(cudaLaunchKernelEx(&cfg, RC_GRAD_KERNEL<NA, RCMARL_LOSS_MSE>, P));
     }
     RC_CUDA(cudaGetLastError());
     return 0;
@@ -475,7 +489,7 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
 // chunks (64 rows) one CTA of this configuration consumes per sweep
 template <int NA>
 static int grad_chunks_per_cta(int loss_mode) {
-    return loss_mode == RCMARL_LOSS_CE ? grad_warps<NA, RCMARL_LOSS_CE>() : grad_warps<NA, RCMARL_LOSS_MSE>();
+    return loss_mode == RCMARL_LOSS_CE ? RC_GRAD_WARPS<NA, RCMARL_LOSS_CE>() : RC_GRAD_WARPS<NA, RCMARL_LOSS_MSE>();
 }
 
 template <int NA>
