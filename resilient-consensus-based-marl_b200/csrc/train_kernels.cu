@@ -29,6 +29,13 @@
 #define RC_GRAD_WARPS grad_warps
 #define RC_GRAD_SMEM grad_smem_floats
 #endif
+// RCMARL_GRAD_TC=1 (make variant_v6): mean-squared-error jobs at n_agents = 5 run on the experimental tensor-core hybrid
+#ifndef RCMARL_GRAD_TC
+#define RCMARL_GRAD_TC 0
+#endif
+#if RCMARL_GRAD_TC
+#include "grad_kernel_tc.cuh"
+#endif
 #include "comm.cuh"
 
 namespace rcmarl {
@@ -473,6 +480,19 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
         cfg.blockDim = dim3(32 * NWC);
         cfg.dynamicSmemBytes = smem_ce;
         RC_CUDA(cudaLaunchKernelEx(&cfg, RC_GRAD_KERNEL<NA, RCMARL_LOSS_CE>, P));
+#if RCMARL_GRAD_TC
+    } else if (NA == 5) {
+        constexpr size_t smem_tc = sizeof(float) * (grad_tc_smem_floats<15>() > grad_tc_smem_floats<10>()
+                                                        ? grad_tc_smem_floats<15>() : grad_tc_smem_floats<10>());
+        static bool attr_tc = false;
+        if (!attr_tc) {
+            if (set_smem(grad_kernel_tc, smem_tc)) return RCMARL_ERR_CUDA;
+            attr_tc = true;
+        }
+        cfg.blockDim = dim3(32 * TC_WARPS);
+        cfg.dynamicSmemBytes = smem_tc;
+        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel_tc, P));
+#endif
     } else {
         if (!attr_mse) {
             if (set_smem(RC_GRAD_KERNEL<NA, RCMARL_LOSS_MSE>, smem_mse)) return RCMARL_ERR_CUDA;
@@ -489,6 +509,9 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
 // chunks (64 rows) one CTA of this configuration consumes per sweep
 template <int NA>
 static int grad_chunks_per_cta(int loss_mode) {
+#if RCMARL_GRAD_TC
+    if (NA == 5 && loss_mode == RCMARL_LOSS_MSE) return 4;      // two 128-row tiles (= four 64-row chunks) per CTA and round
+#endif
     return loss_mode == RCMARL_LOSS_CE ? RC_GRAD_WARPS<NA, RCMARL_LOSS_CE>() : RC_GRAD_WARPS<NA, RCMARL_LOSS_MSE>();
 }
 
