@@ -78,6 +78,13 @@ int64_t rcmarl_param_count(int d_in, int n_out); /* packed length of one network
 /* Scratch needed by the *_grad entry points for `n_jobs` jobs of at most `max_params` parameters. */
 int64_t rcmarl_workspace_bytes(int n_jobs, int max_params);
 
+/* How rcmarl_grad / rcmarl_minibatch_sgd would split a one-wave grid of `sm_count` CTAs over `n_jobs` jobs that sweep
+ * `n_rows` buffer rows: ctas_host[j] = CTAs of job j (kinds_host[j] = RCMARL_IN_*).  balanced = 0: equal shares (the
+ * default of the launchers); 1: shares sized by each job's cost per row (environment switch RCMARL_BALANCED_GRID=1).
+ * Host arithmetic only (no device needed); exposed for tests and for sizing experiments. */
+int rcmarl_grad_grid_plan(int n_agents, const int32_t* kinds_host, int n_jobs, int loss_mode, int64_t n_rows, int balanced,
+                          int sm_count, int32_t* ctas_host);
+
 /* ---------------------------------------------------------------------------
  * K4 / C5.  Coordinate-wise clipped ("winsorised") mean over the neighbour axis,
  * own value = row 0.  Replaces tf.sort/minimum/maximum/clip_by_value/reduce_mean

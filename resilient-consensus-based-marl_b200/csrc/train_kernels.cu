@@ -575,14 +575,15 @@ static bool balanced_grid_enabled() {
     return v != 0;
 }
 
-static int plan_grad_grid(GradParams& P, PartialSlots& S, const int* cost, int64_t nchunks, int gw) {
-    const int n = P.n_jobs, sms = sm_count_cached();
+// g[j] = CTAs of job j; pure host arithmetic (also behind rcmarl_grad_grid_plan for the CPU tests)
+static void plan_shares(int n, const int* cost, int64_t nchunks, int gw, int sms, bool balanced, int* g) {
     int64_t units = (nchunks + gw - 1) / gw;
     if (units < 1) units = 1;
-    int g[RCMARL_MAX_JOBS];
-    if (!balanced_grid_enabled() || n == 1 || n > sms) {
-        const int gy = grid_y_for(units, n, 1);
-        for (int j = 0; j < n; ++j) g[j] = gy;
+    if (!balanced || n == 1 || n > sms) {
+        int64_t gy = sms / n;
+        if (gy < 1) gy = 1;
+        if (gy > units) gy = units;
+        for (int j = 0; j < n; ++j) g[j] = (int)gy;
     } else {
         int used = n;
         for (int j = 0; j < n; ++j) g[j] = 1;
@@ -600,6 +601,12 @@ static int plan_grad_grid(GradParams& P, PartialSlots& S, const int* cost, int64
             ++used;
         }
     }
+}
+
+static int plan_grad_grid(GradParams& P, PartialSlots& S, const int* cost, int64_t nchunks, int gw) {
+    const int n = P.n_jobs;
+    int g[RCMARL_MAX_JOBS];
+    plan_shares(n, cost, nchunks, gw, sm_count_cached(), balanced_grid_enabled(), g);
     int first = 0;
     for (int j = 0; j < n; ++j) {
         P.cta_first[j] = (int16_t)first;
@@ -627,6 +634,22 @@ int64_t rcmarl_workspace_bytes(int n_jobs, int max_params) {
     if (n_jobs < 1) n_jobs = 1;
     const int64_t ctas = (int64_t)sm_count_cached() * 2 + 2 * (int64_t)n_jobs;
     return ctas * (int64_t)(max_params + 1) * (int64_t)sizeof(float);
+}
+
+int rcmarl_grad_grid_plan(int n_agents, const int32_t* kinds_host, int n_jobs, int loss_mode, int64_t n_rows, int balanced,
+                          int sm_count, int32_t* ctas_host) {
+    if ((n_agents != 5 && n_agents != 16) || !kinds_host || !ctas_host || n_jobs < 1 || n_jobs > RCMARL_MAX_JOBS ||
+        n_rows < 0 || sm_count < 1 || (loss_mode != RCMARL_LOSS_MSE && loss_mode != RCMARL_LOSS_CE))
+        return RCMARL_ERR_ARG;
+    int cost[RCMARL_MAX_JOBS], g[RCMARL_MAX_JOBS];
+    for (int j = 0; j < n_jobs; ++j) {
+        if (kinds_host[j] < 0 || kinds_host[j] > 2) return RCMARL_ERR_ARG;
+        cost[j] = grad_job_cost(n_agents, kinds_host[j], loss_mode);
+    }
+    const int cpc = n_agents == 5 ? grad_chunks_per_cta<5>(loss_mode) : grad_chunks_per_cta<16>(loss_mode);
+    plan_shares(n_jobs, cost, (n_rows + 63) / 64, cpc, sm_count, balanced != 0, g);
+    for (int j = 0; j < n_jobs; ++j) ctas_host[j] = g[j];
+    return RCMARL_OK;
 }
 
 int rcmarl_values(const rcmarl_rows* rows, const rcmarl_value_job* jobs, int n_jobs, void* stream) {

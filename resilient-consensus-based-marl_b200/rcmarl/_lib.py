@@ -80,6 +80,8 @@ SYMBOLS = [
     ("rcmarl_device_info", C.c_int, [C.POINTER(C.c_int)] * 3),
     ("rcmarl_param_count", C.c_int64, [C.c_int, C.c_int]),
     ("rcmarl_workspace_bytes", C.c_int64, [C.c_int, C.c_int]),
+    ("rcmarl_grad_grid_plan", C.c_int, [C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int32)]),
     ("rcmarl_clip_mean", C.c_int, [c_fp, C.c_int, C.c_int64, C.c_int64, C.c_int, c_fp, c_fp]),
     ("rcmarl_consensus_hidden", C.c_int, [C.POINTER(ConsensusJob), C.c_int, c_fp]),
     ("rcmarl_values", C.c_int, [C.POINTER(Rows), C.POINTER(ValueJob), C.c_int, c_fp]),

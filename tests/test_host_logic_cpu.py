@@ -93,3 +93,41 @@ def test_packing_and_small_helpers():
     # reward table: float32 division by 5 equals the float64 division rounded to float32 for every reachable value
     d = np.arange(0, 40)
     assert np.array_equal((-(d + 1)).astype(np.float32) / np.float32(5), (-(d + 1) / 5.0).astype(np.float32))
+
+
+def _grid_plan(kinds, n_rows, balanced, na=5, loss=0, sms=148):
+    import ctypes as C
+    from rcmarl import _lib as L
+    k = (C.c_int32 * len(kinds))(*kinds)
+    out = (C.c_int32 * len(kinds))()
+    L.check(L.lib().rcmarl_grad_grid_plan(na, k, len(kinds), loss, n_rows, int(balanced), sms, out), "rcmarl_grad_grid_plan")
+    return list(out)
+
+
+def test_grad_grid_plan_equal_and_balanced_shares():
+    """Host arithmetic of the grad launchers (no device): one wave of at most `sms` CTAs, equal shares by default,
+    cost-balanced shares on request."""
+    from rcmarl import _lib as L
+    SA, S = L.IN_SA, L.IN_S
+    # C2 full-batch fit: 4 team-reward + 4 critic jobs over the 12.288 M buffer rows
+    assert _grid_plan([SA, S] * 4, 12288000, False) == [18] * 8
+    assert _grid_plan([SA, S] * 4, 12288000, True) == [19, 18] * 4
+    # C2 mini-batch step of the malicious agent: 131 072 rows, three chains
+    assert _grid_plan([S, SA, S], 131072, False) == [49, 49, 49]
+    assert _grid_plan([S, SA, S], 131072, True) == [48, 52, 48]          # the team-reward chain drops to 5 rounds
+    # tiny inputs: never more CTAs than 8-chunk work units, never fewer than one
+    assert _grid_plan([SA, S, S], 100, False) == [1, 1, 1]
+    assert _grid_plan([SA, S, S], 100, True) == [1, 1, 1]
+    assert _grid_plan([S], 0, False) == [1]
+    # one wave whatever the mix
+    rs = np.random.RandomState(0)
+    for _ in range(200):
+        n = int(rs.randint(1, 33))
+        kinds = [int(v) for v in rs.randint(0, 3, n)]
+        rows = int(rs.randint(0, 1 << 24))
+        for na in (5, 16):
+            for bal in (False, True):
+                g = _grid_plan(kinds, rows, bal, na=na)
+                assert min(g) >= 1 and sum(g) <= max(148, n), (kinds, rows, na, bal, g)
+    with pytest.raises(L.RcmarlError):
+        _grid_plan([7], 10, False)
