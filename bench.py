@@ -121,10 +121,12 @@ def grad_traffic(workload_name):
     capture (profiles/r01_grad_traffic.json); only valid for the workload it was captured on."""
     if workload_name != "C2":
         return None
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_grad_traffic.json")))["traffic_bytes"]
-    except Exception:
-        return None
+    for name in ("r02_grad_traffic.json", "r01_grad_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))["traffic_bytes"]
+        except Exception:
+            continue
+    return None
 
 
 def measured_peaks():
@@ -135,10 +137,15 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(cfg, rounds, seed=0):
-    """The oracle port of the reference loop (oracle/rpbcac_oracle.py) on the host cores: N = 1 environment
-    (the reference is single-environment), same agents / hyper-parameters / schedule as the GPU arm.
+def cpu_reference_arm(cfg, rounds, seed=0, n_envs=1, threads=None):
+    """The oracle port of the reference loop (oracle/rpbcac_oracle.py) on the host cores with `n_envs` environments
+    (1 = the reference's own shape; > 1 = the batched generalisation of SURVEY Appendix C that the GPU arm runs), same
+    agents / hyper-parameters / schedule as the GPU arm, BLAS limited to `threads` threads (None = library default).
     Returns (agent_updates_per_s, seconds, description)."""
+    if threads is not None:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=int(threads)):
+            return cpu_reference_arm(cfg, rounds, seed, n_envs, None)
     from oracle import rpbcac_oracle as O
     labels, w = cfg["labels"], cfg["weights"]
     NA = len(labels)
@@ -149,15 +156,15 @@ def cpu_reference_arm(cfg, rounds, seed=0):
             agents.append(O.MaliciousOracleAgent(a, c, t, cfg["slow_lr"], cfg["fast_lr"], cfg["gamma"], critic_local_w=w[i][3]))
         else:
             agents.append(O.RPBCACOracleAgent(a, c, t, cfg["slow_lr"], cfg["fast_lr"], cfg["gamma"], H=cfg["H"]))
-    env = O.GridWorldOracle(cfg["nrow"], cfg["ncol"], NA, cfg["desired"], n_envs=1)
+    env = O.GridWorldOracle(cfg["nrow"], cfg["ncol"], NA, cfg["desired"], n_envs=n_envs)
     rs = np.random.RandomState(seed)
     perm_source = O.make_perm_source(seed + 1)
     n_ep, Lq = cfg["n_ep_fixed"], cfg["max_ep_len"]
     S = NS = A = R = None
     # steady-state buffer: two untimed blocks first
     def block():
-        init = rs.randint(0, cfg["nrow"], size=(n_ep, 1, NA, 2))
-        U = rs.rand(n_ep, Lq, 1, NA, 3).astype(np.float32)
+        init = rs.randint(0, cfg["nrow"], size=(n_ep, n_envs, NA, 2))
+        U = rs.rand(n_ep, Lq, n_envs, NA, 3).astype(np.float32)
         return O.rollout_block(env, agents, labels, n_episodes=n_ep, max_ep_len=Lq, gamma=cfg["gamma"], init_states=init, uniforms=U)
     for _ in range(2):
         s, ns, a, r, _e, _r = block()
@@ -166,13 +173,14 @@ def cpu_reference_arm(cfg, rounds, seed=0):
     for _ in range(rounds):
         s, ns, a, r, _e, _r = block()
         S, NS, A, R = tuple(np.concatenate(p) for p in ((S, s), (NS, ns), (A, a), (R, r)))
-        O.update_round(agents, labels, cfg["in_nodes"], S, NS, A, R, n_envs=1, n_epochs=cfg["n_epochs"],
+        O.update_round(agents, labels, cfg["in_nodes"], S, NS, A, R, n_envs=n_envs, n_epochs=cfg["n_epochs"],
                        n_actor_steps=n_ep * Lq, common_reward=False, perm_source=perm_source)
-        keep = cfg["buffer_size"]
+        keep = cfg["buffer_size"] * n_envs
         S, NS, A, R = S[-keep:], NS[-keep:], A[-keep:], R[-keep:]
     dt = time.perf_counter() - t0
-    upd = NA * 1 * Lq * n_ep * rounds
-    return upd / dt, dt, f"{rounds} update round(s) of the oracle loop at n_envs=1 (reference shape), {upd} agent-updates"
+    upd = NA * n_envs * Lq * n_ep * rounds
+    shape = "reference shape" if n_envs == 1 else "batched, SURVEY App. C"
+    return upd / dt, dt, f"{rounds} update round(s) of the oracle loop at n_envs={n_envs} ({shape}), {upd} agent-updates"
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -220,21 +228,31 @@ def main():
         if rank != 0:
             return 0
         ncores = os.cpu_count()
-        import torch
-        torch.set_num_threads(ncores)
+        # The reference is single-environment: its arm runs the oracle port at n_envs = 1 and says so in `config`
+        # (the GPU arm's 4096 environments per GPU are the batched generalisation).  One BLAS thread is the
+        # fastest setting for the (<= 3000 x 20) matrices of this shape (measured: 1 / 4 / 8 threads = 1.86 / 1.11 / 1.60 k/s).
+        ref_config = dict(config, n_envs_per_gpu=1, n_envs_total=1, parallelism="cpu",
+                          l2="n/a (CPU arm)", note="reference shape: ONE environment; not the GPU arm's n_envs")
         vals = []
         t_all = time.perf_counter()
         for _ in range(args.steps):
-            v, dt, desc = cpu_reference_arm(cfg, rounds=1)
+            v, dt, desc = cpu_reference_arm(cfg, rounds=1, n_envs=1, threads=1)
             vals.append(v)
         v = float(np.mean(vals))
+        ms_step = 1000.0 * (time.perf_counter() - t_all) / max(args.steps, 1)
+        # second figure: the same oracle on a batch of environments (vectorised NumPy over rows), 8 BLAS threads
+        nb = int(os.environ.get("RCMARL_CPU_BATCH_ENVS", "16"))
+        bt = min(8, ncores)
+        vb, dtb, descb = cpu_reference_arm(cfg, rounds=1, n_envs=nb, threads=bt)
         line = dict(metric="agent-updates/sec", value=v, unit="agent-updates/s", n_gpus=args.gpus, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=1000.0 * (time.perf_counter() - t_all) / max(args.steps, 1),
+                    warmup=args.warmup, ms_per_step=ms_step,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    impl="reference", config=config,
-                    cpu_baseline=dict(value=v, unit="agent-updates/s", cores=ncores, kind="port",
-                                      sample=desc + " per step; NumPy (BLAS threads = all cores) restatement of the "
-                                      "reference loop -- faster than the original TF-2.4 code path (no Keras retracing)"),
+                    impl="reference", config=ref_config,
+                    cpu_baseline=dict(value=v, unit="agent-updates/s", cores=1, cores_visible=ncores, kind="port",
+                                      sample=desc + " per step; NumPy restatement of the reference loop, 1 BLAS thread "
+                                      "(fastest for this shape) -- faster than the original TF-2.4 code path (no Keras "
+                                      "retracing; the published runs imply 13-19 agent-updates/s, SURVEY 6)"),
+                    cpu_batched=dict(value=vb, unit="agent-updates/s", cores=bt, n_envs=nb, seconds=dtb, sample=descb),
                     e2e=dict(value=v, unit="agent-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         emit(line)
         return 0
@@ -284,6 +302,19 @@ def main():
     ms = float(ms.item())
     clk = clocks.stop() if rank == 0 else {}
     launches = tr.launches - l0
+    # every rank must hold bit-identical replicated parameters after the timed region (weak scaling means nothing if the
+    # replicas drifted apart): all-gather the packed parameters and compare with rank 0's
+    replicas_identical = None
+    if world > 1:
+        mine = torch.cat([tr.actor.flatten(), tr.critic.flatten(), tr.tr.flatten(), tr.critic_local.flatten(),
+                          tr.adam_m.flatten(), tr.adam_v.flatten()])
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        replicas_identical = all(bool(torch.equal(every[0], e)) for e in every[1:])
+        if tr.comm is not None:
+            tr.comm.check()
+        if not replicas_identical:
+            raise SystemExit("bench.py: replicated parameters differ between ranks after the timed region")
     prof = {k: [a.elapsed_time(b) for a, b in v] for k, v in tr.profile.items()}
     tr.profile = None
     value = upd_per_step * world * args.steps / (ms / 1000.0)
@@ -296,27 +327,51 @@ def main():
     fit_ms = float(np.mean(prof["fit_grad"])) if prof.get("fit_grad") else None
     roof = None
     if fit_ms:
-        alg_bytes = 20 * NA * rows_fit                       # SURVEY 8(d): 20*n_agents B per row per lock-step GD step
+        # MAC per buffer row of one fused forward + backward: critic 1 660, team reward 1 860 at 5 agents
+        mac_net = lambda d: (d * 20 + 400 + 20) + (d * 20 + 840)
         d_c, d_t = 2 * NA, 3 * NA
-        mac = n_coop * ((d_c * 20 + 400 + 20) + (d_c * 20 + 400 + 20 + 400 + 20 + 20) +
-                        (d_t * 20 + 400 + 20) + (d_t * 20 + 400 + 20 + 400 + 20 + 20))
-        flops = 2.0 * mac * rows_fit
         try:
             fp32_peak = json.load(open(os.path.join(ROOT, "profiles", "r01_fp32_peak.json")))["fp32_tflops"]
-            fp32_src = "measured on this pool (FFMA2 issue-rate loop, profiles/r01_peak_rates.md)"
+            fp32_src = ("builder-measured on this pool (FFMA2 issue-rate loop, profiles/r01_peak_rates.md); nominal "
+                        "2*128*148*1.965 GHz = 74.4; MEASURED_PEAKS.json has no fp32 entry")
         except Exception:
             fp32_peak = 2 * 128 * 148 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
             fp32_src = "nominal 2*128 lanes*148 SMs*max SM clock"
-        roof = dict(kernel="grad_kernel<5,MSE> (rcmarl_grad, full-batch fit step)", bound="hbm",
-                    achieved=alg_bytes / (fit_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=alg_bytes / (fit_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=grad_traffic(args.workload),
-                    peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", ms_per_launch=fit_ms,
-                    launches_timed=len(prof["fit_grad"]), algorithmic_bytes_per_launch=alg_bytes,
-                    note="this kernel is FP32-FMA bound (350 FLOP/B); see fp32",
-                    fp32=dict(achieved=flops / (fit_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
-                              frac=flops / (fit_ms * 1e-3) / 1e12 / fp32_peak,
-                              peak_source=fp32_src,
-                              algorithmic_flop_per_launch=flops))
+        # regime 1: the full-batch local fits (rcmarl_grad over the whole buffer, 2 nets per cooperative agent)
+        alg_bytes = 20 * NA * rows_fit                       # SURVEY 8(d): 20*n_agents B per row per lock-step GD step
+        flops_fit = 2.0 * n_coop * (mac_net(d_c) + mac_net(d_t)) * rows_fit
+        tf_fit = flops_fit / (fit_ms * 1e-3) / 1e12
+        regimes = dict(full_batch=dict(ms_per_launch=fit_ms, launches_timed=len(prof["fit_grad"]), rows=rows_fit,
+                                       algorithmic_flop_per_launch=flops_fit, achieved=tf_fit, frac=tf_fit / fp32_peak))
+        t_tot, f_tot = float(np.sum(prof["fit_grad"])), flops_fit * len(prof["fit_grad"])
+        # regime 2: the adversaries' mini-batch chains (rcmarl_minibatch_sgd: sequential steps of mb_times x n_envs rows)
+        n_mal = sum(l == "Malicious" for l in cfg["labels"])
+        n_gre = sum(l == "Greedy" for l in cfg["labels"])
+        mac_chain = n_mal * (2 * mac_net(d_c) + mac_net(d_t)) + n_gre * (mac_net(d_c) + mac_net(d_t))
+        if prof.get("minibatch_sgd") and mac_chain:
+            T_buf = rows_fit // N
+            steps_call = tr.mb_epochs * ((T_buf + tr.mb_times - 1) // tr.mb_times)
+            mb_ms = float(np.mean(prof["minibatch_sgd"]))
+            flops_call = 2.0 * mac_chain * tr.mb_epochs * T_buf * N
+            tf_mb = flops_call / (mb_ms * 1e-3) / 1e12
+            regimes["mini_batch"] = dict(us_per_step=1e3 * mb_ms / steps_call, steps_per_call=steps_call,
+                                         calls_timed=len(prof["minibatch_sgd"]), rows_per_step=tr.mb_times * N,
+                                         algorithmic_flop_per_step=flops_call / steps_call, achieved=tf_mb,
+                                         frac=tf_mb / fp32_peak)
+            t_tot += float(np.sum(prof["minibatch_sgd"]))
+            f_tot += flops_call * len(prof["minibatch_sgd"])
+        tf_w = f_tot / (t_tot * 1e-3) / 1e12
+        roof = dict(kernel="grad_kernel<5,MSE> (fused MLP forward/backward; rcmarl_grad + rcmarl_minibatch_sgd)",
+                    bound="fp32", achieved=tf_w, peak=fp32_peak, unit="TFLOP/s", frac=tf_w / fp32_peak,
+                    frac_is="time-weighted over both regimes of the kernel (full-batch fits + mini-batch chains)",
+                    share_of_step=t_tot / ms, traffic=grad_traffic(args.workload),
+                    traffic_note="DRAM bytes of ONE full-batch launch (ncu --set full); compare with hbm_view.algorithmic_bytes_per_launch",
+                    peak_source=fp32_src, regimes=regimes,
+                    hbm_view=dict(achieved=alg_bytes / (fit_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                                  frac=alg_bytes / (fit_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                  algorithmic_bytes_per_launch=alg_bytes,
+                                  peak_source=f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                                  note="full-batch launch; the kernel is FP32-FMA bound (350 FLOP/B), this view is for the record"))
     breakdown = {k: dict(ms_total=float(np.sum(v)), calls=len(v)) for k, v in prof.items()}
 
     # ---- consensus microbench (BASELINE metric part 2, C5): 64 x 1M clip-mean, HBM-bound
@@ -357,16 +412,19 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        v, dt, desc = cpu_reference_arm(cfg, rounds=2)
-        cpu = dict(value=v, unit="agent-updates/s", cores=os.cpu_count(), kind="port", seconds=dt,
-                   sample=desc + "; NumPy restatement of the reference loop (oracle/rpbcac_oracle.py), faster than the "
-                   "original TF-2.4 path")
+        v, dt, desc = cpu_reference_arm(cfg, rounds=2, n_envs=1, threads=1)
+        nb, bt = int(os.environ.get("RCMARL_CPU_BATCH_ENVS", "16")), min(8, os.cpu_count())
+        vb, dtb, descb = cpu_reference_arm(cfg, rounds=1, n_envs=nb, threads=bt)
+        cpu = dict(value=v, unit="agent-updates/s", cores=1, cores_visible=os.cpu_count(), kind="port", seconds=dt,
+                   sample=desc + "; NumPy restatement of the reference loop (oracle/rpbcac_oracle.py), 1 BLAS thread (fastest "
+                   "for the reference's (<= 3000 x 20) matrices); faster than the original TF-2.4 path",
+                   batched=dict(value=vb, unit="agent-updates/s", cores=bt, n_envs=nb, seconds=dtb, sample=descb))
 
     if rank == 0:
         line = dict(metric="agent-updates/sec", value=value, unit="agent-updates/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic", config=config, clocks=clk, e2e=e2e,
-                    gpu_launches=launches, roofline=roof, consensus_roofline=cons, cpu_baseline=cpu,
+                    gpu_launches=launches, replicas_identical=replicas_identical, roofline=roof, consensus_roofline=cons, cpu_baseline=cpu,
                     breakdown_ms=breakdown, update_rounds_per_s=args.steps / (ms / 1000.0))
         emit(line)
     if world > 1:

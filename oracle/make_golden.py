@@ -13,6 +13,11 @@ container (needs /root/reference, which does not exist on the GPU box).
                            verbatim (2 update rounds, 4 coop + 1 malicious, H=1):
                            replay buffer, injected fit permutations, final weights.
 4. ref_env.npz             reference environments/grid_world.py transitions.
+5. ref_adversaries.npz     every Greedy_CAC_agent / Faulty_CAC_agent method
+                           (agents/adversarial_CAC_agents.py:5-72,184-275) executed
+                           verbatim on seeded inputs with injected fit permutations,
+                           plus train_RPBCAC verbatim for 3 cooperative + 1 greedy +
+                           1 faulty agent with common_reward=True (2 update rounds).
 """
 import os
 import re
@@ -34,7 +39,7 @@ import tensorflow as tf                                   # noqa: E402  (the fac
 from tensorflow import keras                              # noqa: E402
 from environments.grid_world import Grid_World            # noqa: E402  (reference, verbatim)
 from agents.resilient_CAC_agents import RPBCAC_agent      # noqa: E402
-from agents.adversarial_CAC_agents import Malicious_CAC_agent   # noqa: E402
+from agents.adversarial_CAC_agents import Malicious_CAC_agent, Greedy_CAC_agent, Faulty_CAC_agent   # noqa: E402
 import training.train_agents as ref_training              # noqa: E402
 
 RAW = os.path.join(REF, "simulation_results", "raw_data")
@@ -286,9 +291,104 @@ def make_env():
     print("env:", len(out), "arrays")
 
 
+def make_adversaries():
+    """Greedy_CAC_agent / Faulty_CAC_agent (agents/adversarial_CAC_agents.py:184-275, :5-72) method vectors and a
+    verbatim train_RPBCAC run with both of them and common_reward=True (the *_global scenarios, train_agents.py:106)."""
+    w, desired = load_w()
+    rs = np.random.RandomState(17)
+    B = 96
+    s, ns, a, r = synth_batch(rs, B)
+    sa = np.concatenate([s, a], -1)
+    out = dict(s=s, ns=ns, a=a, r=r)
+    S, NS, SA = (tf.convert_to_tensor(x, tf.float32) for x in (s, ns, sa))
+    R = tf.convert_to_tensor(r, tf.float32)
+    perm_rs = np.random.RandomState(19)
+    used = []
+
+    def hook(Bn):
+        p = perm_rs.permutation(Bn)
+        used.append(p)
+        return p
+    tf.perm_hook = hook
+    # ---- Greedy: critic / TR mini-batch fits on the local reward, actor fit(batch 200)
+    actor, critic, tr = build_models(w[3])
+    gr = Greedy_CAC_agent(actor, critic, tr, slow_lr=0.002, fast_lr=0.01, gamma=0.9)
+    x, xl = gr.TR_update_local(SA, R[:, 3])
+    y, yl = gr.critic_update_local(S, NS, R[:, 3])
+    big = [np.concatenate([t] * 3, 0) for t in (s, ns, r, a)]          # 288 rows -> 2 actor mini-batches
+    al = gr.actor_update(tf.convert_to_tensor(big[0]), tf.convert_to_tensor(big[1]),
+                         tf.convert_to_tensor(big[2])[:, 3], tf.convert_to_tensor(big[3])[:, 3])
+    for k in range(6):
+        out[f"greedy/tr_k{k}"] = x[k]
+        out[f"greedy/critic_k{k}"] = y[k]
+        out[f"greedy/actor_k{k}"] = actor.get_weights()[k]
+    out["greedy/tr_loss"], out["greedy/critic_loss"], out["greedy/actor_loss"] = np.float32(xl), np.float32(yl), np.float32(al)
+    out["greedy/perms_96"] = np.stack(used[:20])
+    out["greedy/perm_288"] = used[20]
+    gp = gr.get_parameters()
+    out["greedy/n_param_lists"] = np.int64(len(gp))
+    del used[:]
+    # ---- Faulty: only the actor learns; critic / TR are transmitted unchanged
+    actor, critic, tr = build_models(w[4])
+    fa = Faulty_CAC_agent(actor, critic, tr, slow_lr=0.002, gamma=0.9)
+    al = fa.actor_update(tf.convert_to_tensor(big[0]), tf.convert_to_tensor(big[1]),
+                         tf.convert_to_tensor(big[2])[:, 4], tf.convert_to_tensor(big[3])[:, 4])
+    out["faulty/actor_loss"] = np.float32(al)
+    out["faulty/perm_288"] = used[0]
+    for k in range(6):
+        out[f"faulty/actor_k{k}"] = actor.get_weights()[k]
+        out[f"faulty/critic_k{k}"] = fa.get_critic_weights()[k]
+        out[f"faulty/tr_k{k}"] = fa.get_TR_weights()[k]
+    out["faulty/critic_unchanged"] = np.array(all(np.array_equal(p, q) for p, q in zip(fa.get_critic_weights(), w[4][1])))
+    out["faulty/tr_unchanged"] = np.array(all(np.array_equal(p, q) for p, q in zip(fa.get_TR_weights(), w[4][2])))
+    tf.perm_hook = None
+
+    # ---- train_RPBCAC verbatim: 3 cooperative + greedy + faulty, team-average reward for everyone (common_reward)
+    labels = ['Cooperative'] * 3 + ['Greedy', 'Faulty']
+    in_nodes = [[0, 1, 2, 3], [1, 2, 3, 4], [2, 3, 4, 0], [3, 4, 0, 1], [4, 0, 1, 2]]
+    args = dict(n_agents=5, agent_label=labels, in_nodes=in_nodes, n_actions=5, n_states=2,
+                n_episodes=50, max_ep_len=10, n_ep_fixed=25, n_epochs=2, slow_lr=0.002, fast_lr=0.01,
+                batch_size=200, buffer_size=100000, gamma=0.9, H=1, common_reward=True)
+    np.random.seed(6)
+    tf.random.set_seed(6)
+    agents = []
+    for i in range(5):
+        actor, critic, tr = build_models(w[i])
+        if labels[i] == 'Greedy':
+            ag = Greedy_CAC_agent(actor, critic, tr, slow_lr=0.002, fast_lr=0.01, gamma=0.9)
+        elif labels[i] == 'Faulty':
+            ag = Faulty_CAC_agent(actor, critic, tr, slow_lr=0.002, gamma=0.9)
+        else:
+            ag = RPBCAC_agent(actor, critic, tr, slow_lr=0.002, fast_lr=0.01, gamma=0.9, H=1)
+        agents.append(ag)
+    env = Grid_World(nrow=5, ncol=5, n_agents=5, desired_state=desired,
+                     initial_state=np.zeros((5, 2), int), randomize_state=True, scaling=True)
+    perm_rs = np.random.RandomState(23)
+    used = []
+    tf.perm_hook = hook
+    buf = [[], [], [], []]
+    with contextlib.redirect_stdout(io.StringIO()):
+        weights, sim = ref_training.train_RPBCAC(env, agents, args, exp_buffer=buf)
+    tf.perm_hook = None
+    out["run/desired"] = np.asarray(desired, np.int64)
+    out["run/labels"] = np.array(labels)
+    for name, arr in zip(("s", "ns", "a", "r"), buf):
+        out[f"run/{name}"] = np.asarray(arr, np.float32)
+    out["run/n_perms"] = np.int64(len(used))
+    for j, p in enumerate(used):
+        out[f"run/perm{j}"] = p
+    for i in range(5):
+        for n, net in enumerate(weights[i]):
+            for k, arr in enumerate(net):
+                out[f"run/final/agent{i}/n{n}_k{k}"] = np.asarray(arr, np.float32)
+    np.savez_compressed(os.path.join(OUT, "ref_adversaries.npz"), **out)
+    print("adversaries:", len(out), "arrays; train-run perms", len(used))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_kat()
     make_env()
     make_methods()
     make_train_run()
+    make_adversaries()

@@ -19,6 +19,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
     assert d["config"]["workload"] == "C2" and d["config"]["n_agents"] == 5 and d["config"]["H"] == 1
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the arm says what it ran: the reference's single-environment shape, plus a batched figure of the same oracle
+    assert d["config"]["n_envs_per_gpu"] == 1 and d["config"]["n_envs_total"] == 1
+    assert d["cpu_batched"]["n_envs"] > 1 and d["cpu_batched"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -129,3 +129,78 @@ def test_update_rounds_match_reference_train_run():
         for n in range(len(final[i])):
             for k in range(6):
                 close(got[n][k], final[i][n][k], rtol=5e-4, atol=2e-5)
+
+
+def test_greedy_methods_match_reference():
+    """Greedy_CAC_agent (agents/adversarial_CAC_agents.py:184-275) executed verbatim on the facade vs the oracle class."""
+    z = load("ref_adversaries.npz")
+    w, _, _ = pretrained()
+    s, ns, a, r = z["s"], z["ns"], z["a"], z["r"]
+    sa = np.concatenate([s, a], -1)
+    perms = z["greedy/perms_96"]
+    gr = O.GreedyOracleAgent(w[3][0], w[3][1], w[3][2], 0.002, 0.01, gamma=0.9)
+    x, xl = gr.TR_update_local(sa, r[:, 3], perms[0:10])
+    y, yl = gr.critic_update_local(s, ns, r[:, 3], perms[10:20])
+    big = [np.concatenate([t] * 3, 0) for t in (s, ns, r, a)]
+    al = gr.actor_update(big[0], big[1], big[2][:, 3], big[3][:, 3], z["greedy/perm_288"])
+    for k in range(6):
+        close(x[k], z[f"greedy/tr_k{k}"], rtol=2e-4, atol=5e-6)
+        close(y[k], z[f"greedy/critic_k{k}"], rtol=2e-4, atol=5e-6)
+        close(gr.actor[k], z[f"greedy/actor_k{k}"], rtol=2e-4, atol=5e-6)
+    close(xl, z["greedy/tr_loss"], rtol=1e-4)
+    close(yl, z["greedy/critic_loss"], rtol=1e-4)
+    close(al, z["greedy/actor_loss"], rtol=1e-4, atol=1e-6)
+    assert len(gr.get_parameters()) == int(z["greedy/n_param_lists"]) == 3
+
+
+def test_faulty_methods_match_reference():
+    """Faulty_CAC_agent (agents/adversarial_CAC_agents.py:5-72): only the actor learns, critic / TR are transmitted as is."""
+    z = load("ref_adversaries.npz")
+    w, _, _ = pretrained()
+    s, ns, a, r = z["s"], z["ns"], z["a"], z["r"]
+    assert bool(z["faulty/critic_unchanged"]) and bool(z["faulty/tr_unchanged"])
+    fa = O.FaultyOracleAgent(w[4][0], w[4][1], w[4][2], 0.002, gamma=0.9)
+    big = [np.concatenate([t] * 3, 0) for t in (s, ns, r, a)]
+    al = fa.actor_update(big[0], big[1], big[2][:, 4], big[3][:, 4], z["faulty/perm_288"])
+    close(al, z["faulty/actor_loss"], rtol=1e-4, atol=1e-6)
+    for k in range(6):
+        close(fa.actor[k], z[f"faulty/actor_k{k}"], rtol=2e-4, atol=5e-6)
+        assert np.array_equal(fa.get_critic_weights()[k], z[f"faulty/critic_k{k}"])
+        assert np.array_equal(fa.get_TR_weights()[k], z[f"faulty/tr_k{k}"])
+
+
+def test_update_rounds_with_greedy_and_faulty_match_reference_train_run():
+    """Reference train_RPBCAC verbatim with 3 cooperative + 1 greedy + 1 faulty agent and common_reward=True
+    (train_agents.py:106; the *_global scenarios), replayed through oracle.update_round."""
+    z = load("ref_adversaries.npz")
+    w, desired, _ = pretrained()
+    labels = [str(x) for x in z["run/labels"]]
+    assert np.array_equal(desired, z["run/desired"])
+    in_nodes = [[0, 1, 2, 3], [1, 2, 3, 4], [2, 3, 4, 0], [3, 4, 0, 1], [4, 0, 1, 2]]
+    agents = []
+    for i, l in enumerate(labels):
+        if l == "Greedy":
+            agents.append(O.GreedyOracleAgent(w[i][0], w[i][1], w[i][2], 0.002, 0.01, 0.9))
+        elif l == "Faulty":
+            agents.append(O.FaultyOracleAgent(w[i][0], w[i][1], w[i][2], 0.002, 0.9))
+        else:
+            agents.append(O.RPBCACOracleAgent(w[i][0], w[i][1], w[i][2], 0.002, 0.01, 0.9, H=1))
+    perms = [z[f"run/perm{j}"] for j in range(int(z["run/n_perms"]))]
+    it = iter(perms)
+
+    def perm_source(T):
+        p = next(it)
+        assert len(p) == T
+        return p
+    for rnd in (1, 2):
+        B = 250 * rnd
+        O.update_round(agents, labels, in_nodes, z["run/s"][:B], z["run/ns"][:B], z["run/a"][:B], z["run/r"][:B],
+                       n_envs=1, n_epochs=2, n_actor_steps=250, common_reward=True, perm_source=perm_source)
+    assert next(it, None) is None
+    final = agent_weights(z, "run/final")
+    for i in range(5):
+        got = agents[i].get_parameters()
+        assert len(got) == len(final[i]) == 3
+        for n in range(3):
+            for k in range(6):
+                close(got[n][k], final[i][n][k], rtol=5e-4, atol=2e-5)
