@@ -18,20 +18,15 @@ struct CommHost {
 static CommHost* g_bound = nullptr;
 CommHost* comm_bound() { return g_bound; }
 
-static size_t data_bytes(const CommHost* c) { return sizeof(float) * 2 * (size_t)c->world * (size_t)c->max_floats; }
-static size_t total_bytes(const CommHost* c) { return data_bytes(c) + sizeof(uint32_t) * (COMM_MAX_WORLD + 8); }
+static size_t data_bytes(const CommHost* c) { return sizeof(uint2) * 2 * (size_t)c->world * (size_t)c->max_floats; }
+static size_t total_bytes(const CommHost* c) { return data_bytes(c) + sizeof(uint32_t) * 8; }
 
 bool comm_next(CommDev* out, int64_t need_floats) {
     CommHost* c = g_bound;
     if (!c || !c->connected || need_floats > c->max_floats) return false;
     c->seq += 1;
-    for (int p = 0; p < c->world; ++p) {
-        out->data[p] = (float*)c->peer_base[p];
-        out->flags[p] = (uint32_t*)((char*)c->peer_base[p] + data_bytes(c));
-    }
-    uint32_t* local_flags = (uint32_t*)((char*)c->base + data_bytes(c));
-    out->counter = local_flags + COMM_MAX_WORLD;
-    out->error = local_flags + COMM_MAX_WORLD + 1;
+    for (int p = 0; p < COMM_MAX_WORLD; ++p) out->cells[p] = p < c->world ? (uint2*)c->peer_base[p] : nullptr;
+    out->error = (uint32_t*)((char*)c->base + data_bytes(c));
     out->max_floats = c->max_floats;
     out->rank = c->rank;
     out->world = c->world;
@@ -91,7 +86,7 @@ int rcmarl_comm_error(void* comm) {
     CommHost* c = (CommHost*)comm;
     if (!c) return RCMARL_ERR_ARG;
     uint32_t e = 0;
-    RC_CUDA(cudaMemcpy(&e, (char*)c->base + data_bytes(c) + sizeof(uint32_t) * (COMM_MAX_WORLD + 1), sizeof(e), cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(&e, (char*)c->base + data_bytes(c), sizeof(e), cudaMemcpyDeviceToHost));
     return (int)e;
 }
 

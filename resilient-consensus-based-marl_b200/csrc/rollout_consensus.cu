@@ -47,9 +47,21 @@ struct Track {
         for (int i = 0; i < H; ++i) { const float hi = fmaxf(large[i], c); c = fminf(large[i], c); large[i] = hi; }
         large[H] = fmaxf(large[H], c);
     }
-    __device__ __forceinline__ float finish(float own, int n) const {
-        const float lo = fminf(small[H], own);
-        const float hi = fmaxf(large[H], own);
+    __device__ __forceinline__ void window(float own, float& lo, float& hi) const {
+        lo = fminf(small[H], own);
+        hi = fmaxf(large[H], own);
+    }
+    // The single-pass identity subtracts the excess of the extremes from a running sum that CONTAINS them: exact in real
+    // arithmetic, but in fp32 one huge (adversarial) value absorbs the honest ones before it cancels (0.1 + 1e8 - 1e8 = 0),
+    // and an infinity gives inf - inf.  The identity is therefore only used while the most extreme value stays within
+    // 16x of the clipping window (error <= 16 n eps of the window, the order of the reference's own fp32 mean); otherwise the
+    // caller re-reads the column and sums clip(v, lo, hi) directly (second pass, taken for outlier columns only).
+    __device__ __forceinline__ bool identity_ok(float lo, float hi) const {
+        const float w = fmaxf(fabsf(lo), fabsf(hi));
+        const float m = fmaxf(fabsf(small[0]), fabsf(large[0]));
+        return m <= 16.f * w;                 // false for NaN / inf extremes and for w == 0 < m
+    }
+    __device__ __forceinline__ float finish(float lo, float hi, int n) const {
         float s = sum;
 #pragma unroll
         for (int i = 0; i <= H; ++i) {
@@ -59,6 +71,8 @@ struct Track {
         return s / (float)n;
     }
 };
+// tf.clip_by_value(x, lo, hi) = max(min(x, hi), lo)   (agents/resilient_CAC_agents.py:55)
+__device__ __forceinline__ float clip1(float v, float lo, float hi) { return fmaxf(fminf(v, hi), lo); }
 
 // ---- sorting networks (optimal comparator counts, verified with the 0-1 principle in tools/gen_sortnets.py) ----
 template <bool ASC>
@@ -138,9 +152,23 @@ __global__ void __launch_bounds__(256) clip_mean_vec4_kernel(const float* __rest
         if (k == 0) own = v;
         t[0].push(v.x); t[1].push(v.y); t[2].push(v.z); t[3].push(v.w);
     }
+    float lo[4], hi[4];
+    t[0].window(own.x, lo[0], hi[0]); t[1].window(own.y, lo[1], hi[1]);
+    t[2].window(own.z, lo[2], hi[2]); t[3].window(own.w, lo[3], hi[3]);
     float4 r;
-    r.x = t[0].finish(own.x, n); r.y = t[1].finish(own.y, n);
-    r.z = t[2].finish(own.z, n); r.w = t[3].finish(own.w, n);
+    if (t[0].identity_ok(lo[0], hi[0]) && t[1].identity_ok(lo[1], hi[1]) && t[2].identity_ok(lo[2], hi[2]) &&
+        t[3].identity_ok(lo[3], hi[3])) {
+        r.x = t[0].finish(lo[0], hi[0], n); r.y = t[1].finish(lo[1], hi[1], n);
+        r.z = t[2].finish(lo[2], hi[2], n); r.w = t[3].finish(lo[3], hi[3], n);
+    } else {                                   // outlier column(s): second pass, clip first, then sum (reference order)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int kk = 0; kk < n; ++kk) {
+            const float4 v = ld_stream(base + (int64_t)kk * rs4);
+            s0 += clip1(v.x, lo[0], hi[0]); s1 += clip1(v.y, lo[1], hi[1]);
+            s2 += clip1(v.z, lo[2], hi[2]); s3 += clip1(v.w, lo[3], hi[3]);
+        }
+        r.x = s0 / (float)n; r.y = s1 / (float)n; r.z = s2 / (float)n; r.w = s3 / (float)n;
+    }
     reinterpret_cast<float4*>(out)[c] = r;
 }
 
@@ -157,7 +185,15 @@ __global__ void __launch_bounds__(256) clip_mean_scalar_kernel(const float* __re
         if (k == 0) own = v;
         t.push(v);
     }
-    out[c] = t.finish(own, n);
+    float lo, hi;
+    t.window(own, lo, hi);
+    if (t.identity_ok(lo, hi)) {
+        out[c] = t.finish(lo, hi, n);
+    } else {
+        float sum = 0.f;
+        for (int k = 0; k < n; ++k) sum += clip1(__ldg(vals + (int64_t)k * row_stride + c), lo, hi);
+        out[c] = sum / (float)n;
+    }
 }
 
 template <int H>

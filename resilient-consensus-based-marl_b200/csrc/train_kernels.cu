@@ -215,6 +215,7 @@ struct ReduceCommParams {
     rcmarl_sgd_job sgd[RCMARL_MAX_JOBS];
     PartialSlots slots;
     int32_t out_stride, fuse_sgd;     // out_stride: distance between the jobs' blocks in the exchange buffer
+    int32_t n_jobs, max_n;            // items = n_jobs x ceil(max_n / 32)
     CommDev comm;
 };
 __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant__ ReduceCommParams P) {
@@ -223,28 +224,40 @@ __global__ void __launch_bounds__(256) reduce_comm_kernel(const __grid_constant_
 #if RCMARL_PDL_REDUCE
     pdl_wait();
 #endif
-    const int j = blockIdx.y;
-    const int i = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int nj = P.n[j];
-    const bool valid = i < nj;
-    const int64_t off = (int64_t)j * P.out_stride + i;
-    const float s = block_partial_sum(P.partial, P.slots, j, i, valid, sh);
-    if (threadIdx.x < 32 && valid) comm_push(P.comm, off, s);
-    comm_publish_and_wait(P.comm, gridDim.x * gridDim.y);
-    if (threadIdx.x < 32 && valid) {
-        const float tot = comm_total(P.comm, off);
-        if (P.sums[j]) P.sums[j][i] = tot;
-        if (P.fuse_sgd) {
-            const rcmarl_sgd_job& job = P.sgd[j];
-            if (i < job.n) {
-                const float v = job.src[i];
-                job.dst[i] = i >= job.first ? v - job.coef * tot : v;
-            } else if (i == job.n && job.loss_out) {
-                const float l = job.loss_coef * tot;
-                *job.loss_out = job.loss_accumulate ? *job.loss_out + l : l;
+    // One item = 32 consecutive elements of one job.  Items are independent (comm.cuh): a CTA walks its items in
+    // ascending order on every rank, so any grid size is deadlock-free and nothing has to be co-resident.
+    const int blocks_per_job = (P.max_n + 31) / 32;
+    const int n_items = blocks_per_job * P.n_jobs;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int j = item / blocks_per_job;
+        const int i = (item - j * blocks_per_job) * 32 + (threadIdx.x & 31);
+        const bool valid = i < P.n[j];
+        const int64_t off = (int64_t)j * P.out_stride + i;
+        const float s = block_partial_sum(P.partial, P.slots, j, i, valid, sh);
+        if (threadIdx.x < 32 && valid) {
+            comm_push(P.comm, off, s);
+            const float tot = comm_wait_total(P.comm, off);
+            if (P.sums[j]) P.sums[j][i] = tot;
+            if (P.fuse_sgd) {
+                const rcmarl_sgd_job& job = P.sgd[j];
+                if (i < job.n) {
+                    const float v = job.src[i];
+                    job.dst[i] = i >= job.first ? v - job.coef * tot : v;
+                } else if (i == job.n && job.loss_out) {
+                    const float l = job.loss_coef * tot;
+                    *job.loss_out = job.loss_accumulate ? *job.loss_out + l : l;
+                }
             }
         }
+        __syncthreads();          // sh[] is reused by the next item
     }
+}
+
+// grid of reduce_comm_kernel: one CTA per item up to two resident CTAs per SM
+static dim3 reduce_comm_grid(int max_n, int n_jobs) {
+    const int items = ((max_n + 31) / 32) * n_jobs;
+    const int cap = sm_count_cached() * 2;
+    return dim3(items < cap ? items : cap);
 }
 
 // ============================================================================================
@@ -710,9 +723,9 @@ int rcmarl_grad(const rcmarl_rows* rows, const rcmarl_grad_job* jobs, int n_jobs
     if (comm_bound()) {
         ReduceCommParams C;
         if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
-        C.partial = Q.partial; C.slots = Q.slots; C.out_stride = maxn; C.fuse_sgd = 0;
+        C.partial = Q.partial; C.slots = Q.slots; C.out_stride = maxn; C.fuse_sgd = 0; C.n_jobs = n_jobs; C.max_n = maxn;
         for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
-        reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
+        if (launch_reduce(reduce_comm_kernel, C, reduce_comm_grid(maxn, n_jobs), st)) return RCMARL_ERR_CUDA;
     } else {
         reduce_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(Q);
     }
@@ -772,16 +785,14 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
             if (comm_bound()) {
                 ReduceCommParams C;
                 if (!comm_next(&C.comm, (int64_t)n_jobs * maxn)) return RCMARL_ERR_ARG;
-                C.partial = Q.partial; C.slots = Q.slots; C.out_stride = maxn; C.fuse_sgd = 1;
+                C.partial = Q.partial; C.slots = Q.slots; C.out_stride = maxn; C.fuse_sgd = 1; C.n_jobs = n_jobs; C.max_n = maxn;
                 for (int j = 0; j < n_jobs; ++j) {
                     C.sums[j] = nullptr;
                     C.n[j] = Q.jobs[j].n + 1;
                     C.sgd[j] = Q.jobs[j];
                     C.sgd[j].coef = lr * 2.0f / ((float)n_rows * (float)C.comm.world);   // global batch
                 }
-                // plain launch: the PDL-launched form was only measured on one GPU (profiles/r01_late_variants.md)
-                reduce_comm_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, st>>>(C);
-                RC_CUDA(cudaGetLastError());
+                if (launch_reduce(reduce_comm_kernel, C, reduce_comm_grid(maxn, n_jobs), st)) return RCMARL_ERR_CUDA;
             } else {
                 if (launch_reduce(reduce_sgd_kernel, Q, dim3((maxn + 31) / 32, n_jobs), st)) return RCMARL_ERR_CUDA;
             }
@@ -829,9 +840,9 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
         if (comm_bound()) {
             ReduceCommParams C;
             if (!comm_next(&C.comm, (int64_t)n_jobs * TEAM_N)) return RCMARL_ERR_ARG;
-            C.partial = Q.partial; C.slots = Q.slots; C.out_stride = TEAM_N; C.fuse_sgd = 0;
+            C.partial = Q.partial; C.slots = Q.slots; C.out_stride = TEAM_N; C.fuse_sgd = 0; C.n_jobs = n_jobs; C.max_n = TEAM_N;
             for (int j = 0; j < n_jobs; ++j) { C.sums[j] = Q.sums[j]; C.n[j] = Q.n[j]; }
-            reduce_comm_kernel<<<dim3((TEAM_N + 31) / 32, n_jobs), 256, 0, st>>>(C);
+            if (launch_reduce(reduce_comm_kernel, C, reduce_comm_grid(TEAM_N, n_jobs), st)) return RCMARL_ERR_CUDA;
         } else {
             reduce_kernel<<<dim3((TEAM_N + 31) / 32, n_jobs), 256, 0, st>>>(Q);
         }

@@ -15,14 +15,23 @@ class PeerComm:
         lib = L.lib()
         self.rank, self.world = rank, world
         h = C.c_void_p()
-        L.check(lib.rcmarl_comm_create(rank, world, max_floats, C.byref(h)), "rcmarl_comm_create")
-        self.handle = h
         nb = lib.rcmarl_comm_handle_bytes()
         buf = C.create_string_buffer(nb)
-        L.check(lib.rcmarl_comm_export(h, buf), "rcmarl_comm_export")
+        # create + export may fail on one rank only (out of memory, IPC disabled): every rank still takes part in the
+        # gather below and all of them see the failure, so the collectives stay matched and nobody hangs
+        st = lib.rcmarl_comm_create(rank, world, max_floats, C.byref(h))
+        if st == 0:
+            st = lib.rcmarl_comm_export(h, buf)
+        self.handle = h if h.value else None
         gathered = [None] * world
-        dist.all_gather_object(gathered, bytes(buf.raw), group=group)
-        status = lib.rcmarl_comm_connect(h, b"".join(gathered))
+        dist.all_gather_object(gathered, (int(st), bytes(buf.raw)), group=group)
+        if any(g[0] != 0 for g in gathered):
+            if self.handle is not None:
+                lib.rcmarl_comm_destroy(self.handle)
+                self.handle = None
+            bad = [r for r, g in enumerate(gathered) if g[0] != 0]
+            raise L.RcmarlError(f"rcmarl_comm_create / export failed on rank(s) {bad}")
+        status = lib.rcmarl_comm_connect(h, b"".join(g[1] for g in gathered))
         torch.cuda.synchronize()
         dist.barrier(group=group)                     # every rank has mapped (or failed to map) every buffer
         if status != 0:

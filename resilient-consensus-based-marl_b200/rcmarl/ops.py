@@ -212,16 +212,25 @@ def reward_mix(r, agents, out=None, scale=1.0):
     return out
 
 
-def state_tables(nrow, ncol):
-    """(i - mean) / std per coordinate in float64, rounded to float32 (grid_world.py:30-35,70)."""
+def state_tables(nrow, ncol, scaling=True):
+    """(i - mean) / std per coordinate in float64, rounded to float32 (grid_world.py:30-35,70); mean / std are taken over
+    the axis' own range, but both tables cover max(nrow, ncol) positions because the reference clips BOTH coordinates
+    with nrow - 1 (grid_world.py:55), so y can leave [0, ncol) when nrow > ncol.  scaling=False: identity (the
+    reference's Grid_World default)."""
+    n = max(nrow, ncol)
+    idx = np.arange(n)
+    if not scaling:
+        t = idx.astype(np.float32)
+        return t, t.copy()
     x, y = np.arange(nrow), np.arange(ncol)
-    tx = ((x - np.mean(x)) / np.std(x)).astype(np.float32)
-    ty = ((y - np.mean(y)) / np.std(y)).astype(np.float32)
+    tx = ((idx - np.mean(x)) / np.std(x)).astype(np.float32)
+    ty = ((idx - np.mean(y)) / np.std(y)).astype(np.float32)
     return tx, ty
 
 
 def rollout(actor_w, critic_w, desired, sa, ns, r, time_begin, est, ret, *, n_envs, n_agents, n_episodes, max_ep_len,
-            nrow, ncol, gamma, mu=0.1, seed=0, env_offset=0, episode_offset=0, uniforms=None, init_state=None):
+            nrow, ncol, gamma, mu=0.1, seed=0, env_offset=0, episode_offset=0, uniforms=None, init_state=None,
+            scaling=True):
     A = L.RolloutArgs()
     A.actor_w, A.critic_w, A.desired = actor_w.data_ptr(), critic_w.data_ptr(), desired.data_ptr()
     A.sa, A.ns, A.r = sa.data_ptr(), ns.data_ptr(), r.data_ptr()
@@ -231,10 +240,11 @@ def rollout(actor_w, critic_w, desired, sa, ns, r, time_begin, est, ret, *, n_en
     A.seed, A.env_offset, A.episode_offset = int(seed), int(env_offset), int(episode_offset)
     A.n_envs, A.n_agents, A.n_episodes, A.max_ep_len = n_envs, n_agents, n_episodes, max_ep_len
     A.nrow, A.ncol, A.gamma, A.mu = nrow, ncol, gamma, mu
-    tx, ty = state_tables(nrow, ncol)
-    for i in range(nrow):
+    if max(nrow, ncol) > L.MAX_GRID:
+        raise L.RcmarlError(f"grid {nrow}x{ncol} exceeds RCMARL_MAX_GRID = {L.MAX_GRID}")
+    tx, ty = state_tables(nrow, ncol, scaling)
+    for i in range(len(tx)):
         A.state_tab_x[i] = float(tx[i])
-    for i in range(ncol):
         A.state_tab_y[i] = float(ty[i])
     L.check(L.lib().rcmarl_rollout(C.byref(A), _stream()), "rcmarl_rollout")
 

@@ -27,7 +27,7 @@ class Trainer:
                  fast_lr=0.01, slow_lr=0.01, max_ep_len=20, n_ep_fixed=50, n_epochs=10, buffer_size=2000,
                  common_reward=False, mu=0.1, seed=0, device=None, rank=0, world=1, group=None,
                  perm_source=None, local_steps=5, mb_epochs=10, mb_times=32, actor_mb_times=200,
-                 capacity_times=None, adam_state=None):
+                 capacity_times=None, adam_state=None, scaling=True, fixed_initial_state=None):
         L.lib()
         self.labels = list(labels)
         self.NA = NA = len(self.labels)
@@ -50,6 +50,10 @@ class Trainer:
         self._perm_gen = torch.Generator(device="cpu")
         self._perm_gen.manual_seed(self.seed * 7919 + 17)
         self.episodes_done = 0
+        # Grid_World(scaling=..., randomize_state=False, initial_state=...) of the reference (grid_world.py:21-45)
+        self.scaling = bool(scaling)
+        self.fixed_initial_state = None if fixed_initial_state is None else np.asarray(fixed_initial_state, np.int32).reshape(NA, 2)
+        self._fixed_init_dev = None
 
         self.PA, self.PC, self.PT = L.param_count(2 * NA, 5), L.param_count(2 * NA, 1), L.param_count(3 * NA, 1)
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -188,10 +192,15 @@ class Trainer:
 
     def _rollout_launch(self, est, ret, n_ep, uniforms, init_state):
         Lq = self.max_ep_len
+        if init_state is None and self.fixed_initial_state is not None:    # randomize_state=False: every reset -> initial_state
+            if self._fixed_init_dev is None or self._fixed_init_dev.shape[0] < n_ep:
+                host = np.broadcast_to(self.fixed_initial_state, (n_ep, self.N, self.NA, 2))
+                self._fixed_init_dev = torch.as_tensor(np.ascontiguousarray(host)).to(self.dev)
+            init_state = self._fixed_init_dev
         ops.rollout(self.actor, self.critic, self.desired, self.sa, self.ns, self.r, self.t_filled, est, ret,
                     n_envs=self.N, n_agents=self.NA, n_episodes=n_ep, max_ep_len=Lq, nrow=self.nrow, ncol=self.ncol,
                     gamma=self.gamma, mu=self.mu, seed=self.seed, env_offset=self.rank * self.N,
-                    episode_offset=self.episodes_done, uniforms=uniforms, init_state=init_state)
+                    episode_offset=self.episodes_done, uniforms=uniforms, init_state=init_state, scaling=self.scaling)
 
     def load_rows(self, s, ns, a, r):
         """Append externally produced transitions (exp_buffer, train_agents.py:36-40; parity tests; bench e2e).
@@ -463,7 +472,7 @@ class Trainer:
         torch.save(self.state_dict(include_buffer), path)
 
     def load(self, path):
-        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
 
     def trim(self):
         """Keep the newest `buffer_size` time rows (train_agents.py:158-163): chunked, non-overlapping

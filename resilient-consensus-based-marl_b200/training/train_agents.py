@@ -41,7 +41,10 @@ def build_trainer(env, agents, args, exp_buffer=None, **overrides):
     adam = [(ag.adam.m, ag.adam.v, ag.adam.t) if getattr(ag, 'adam', None) is not None and ag.adam.m is not None else None
             for ag in agents]
     rank, world = _dist_info()
-    kw = dict(labels=labels, in_nodes=args['in_nodes'], weights=weights, desired=env.desired_state,
+    # Grid_World options of the reference (grid_world.py:21-45): state scaling and fixed / random resets
+    scaling = bool(np.any(np.asarray(getattr(env, 'std_state', 1)) != 1) or np.any(np.asarray(getattr(env, 'mean_state', 0)) != 0))
+    fixed0 = None if getattr(env, 'randomize_state', True) else env.initial_state
+    kw = dict(scaling=scaling, fixed_initial_state=fixed0, labels=labels, in_nodes=args['in_nodes'], weights=weights, desired=env.desired_state,
               n_envs=getattr(env, 'n_envs', 1), nrow=env.nrow, ncol=env.ncol, gamma=args['gamma'], H=H[0] if H else 0,
               fast_lr=fast[0] if fast else args.get('fast_lr', 0.01), slow_lr=slow_lr, max_ep_len=args['max_ep_len'],
               n_ep_fixed=args['n_ep_fixed'], n_epochs=args['n_epochs'], buffer_size=args['buffer_size'],

@@ -71,6 +71,28 @@ def test_clip_mean_matches_oracle(K, n, H, P):
         close(got, v.astype(np.float64).mean(0), rtol=0, atol=4e-6 * np.abs(v).max())
 
 
+@pytest.mark.parametrize("n,H,P", [(4, 1, 640), (6, 2, 1421), (64, 4, 4096), (64, 1, 4099), (4, 0, 64)])
+def test_clip_mean_is_robust_to_adversarial_outliers(K, n, H, P):
+    """One Byzantine neighbour sends 1e8 / -3e30 / +-inf: tf.clip_by_value clips first and averages afterwards
+    (agents/resilient_CAC_agents.py:55-56), so with H >= 1 the result stays at the honest values.  ABSOLUTE tolerance
+    (not scaled by max|v|): a single-pass sum that contains the outlier would lose the honest values entirely."""
+    rs = np.random.RandomState(n + H)
+    v = (0.1 + 0.01 * rs.randn(n, P)).astype(np.float32)
+    bad = [1e8, -3e30, np.inf, -np.inf]
+    for j in range(P):
+        if j % 3 == 0 and n > 1:
+            v[1 + (j % (n - 1)), j] = bad[(j // 3) % 4]      # never the own row
+    want = O.resilient_aggregation(v.astype(np.float64), H)
+    got = K.ops.clip_mean(to_dev(K, v)[0], H).cpu().numpy().astype(np.float64)
+    if H >= 1:
+        assert np.isfinite(want).all() and np.abs(want - 0.1).max() < 0.1
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+    else:                                                        # H = 0 is the plain mean: outliers pass through
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=1e-5, atol=2e-6)
+        assert np.array_equal(np.isinf(got[~fin]) | np.isnan(got[~fin]), np.ones((~fin).sum(), bool))
+
+
 def test_clip_mean_rejects_bad_args(K):
     v = torch.zeros(4, 8, device=K.dev)
     with pytest.raises(K.L.RcmarlError):

@@ -174,3 +174,28 @@ def test_c3_shape_update_round_matches_oracle():
         np.testing.assert_allclose(got[k], want[k], rtol=2e-3, atol=2e-5, err_msg=k)
     for i in range(NA):
         close_w(tr.get_weights(i), agents[i].get_parameters())
+
+
+def test_env_options_scaling_off_and_fixed_initial_state():
+    """Grid_World(scaling=False, randomize_state=False, initial_state=...) of the reference (grid_world.py:21-45): the
+    rollout feeds raw integer positions and every episode starts from initial_state; nrow > ncol keeps both
+    coordinates clipped with nrow - 1 (:55) and scaled with their own axis statistics."""
+    need_gpu()
+    from rcmarl.trainer import Trainer
+    from rcmarl import ops
+    w, desired, labels = pretrained()
+    init = np.array([[0, 1], [4, 4], [2, 3], [1, 0], [3, 2]])
+    tr = Trainer(labels=labels, in_nodes=IN_NODES, weights=w, desired=desired, n_envs=16, gamma=0.9, H=1, max_ep_len=6,
+                 n_ep_fixed=4, n_epochs=1, buffer_size=100, scaling=False, fixed_initial_state=init)
+    tr.rollout_block()
+    sa = tr.sa[:4 * 6 * 16].cpu().numpy().reshape(4, 6, 16, 5, 3)
+    assert np.array_equal(sa[:, 0, :, :, :2], np.broadcast_to(init.astype(np.float32), (4, 16, 5, 2)))
+    assert set(np.unique(sa[..., :2])) <= {0.0, 1.0, 2.0, 3.0, 4.0}
+    tx, ty = ops.state_tables(7, 4)
+    assert len(tx) == len(ty) == 7 and np.isclose(ty[6], (6 - 1.5) / np.std(np.arange(4)))
+    tall = Trainer(labels=labels, in_nodes=IN_NODES, weights=w, desired=np.minimum(desired, 3), n_envs=64, nrow=7, ncol=4,
+                   gamma=0.9, H=1, max_ep_len=20, n_ep_fixed=6, n_epochs=1, buffer_size=200, seed=3)
+    tall.rollout_block()
+    ns_y = tall.ns[:20 * 6 * 64].cpu().numpy().reshape(-1, 5, 2)[:, :, 1]
+    assert set(np.unique(ns_y)) <= set(ty.tolist())          # no zero table entries: every reachable y is scaled
+    assert ns_y.max() > ty[3] + 1e-6                          # ... and y does leave [0, ncol)
