@@ -187,6 +187,22 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows_host, const rcmarl_grad_job* gj
                          const rcmarl_sgd_job* sjobs_host, int n_jobs, int epochs, int n_times, int mb_times,
                          float lr, void* ws, int64_t ws_bytes, void* stream);
 
+/* The same fit as ONE persistent kernel (csrc/minibatch_persist.cuh): the CTAs stay resident for all epochs x
+ * mini-batches, every chain's parameters live in the shared memory of its CTAs, and the per-step reduction over CTAs
+ * (and, with a bound exchange context, over ranks through NVLink peer memory) runs through {value, sequence} cells
+ * instead of kernel boundaries -- no launches, no grid barrier, no atomics; results are bitwise reproducible and
+ * identical on every rank.  Arguments as rcmarl_minibatch_sgd, except:
+ *   sjobs[j].coef > 0 overrides `lr` for chain j (per-agent fast_lr, agents/resilient_CAC_agents.py:36);
+ *   cells / cells_bytes: caller-owned scratch of rcmarl_minibatch_cells_bytes() bytes that must be ZERO before the
+ *     first call and is otherwise only touched by this entry point;
+ *   seq_first >= 1: first of the `rcmarl_minibatch_steps()` consecutive sequence numbers this call consumes; the
+ *     caller passes strictly increasing, non-overlapping ranges over the lifetime of `cells`. */
+int64_t rcmarl_minibatch_cells_bytes(int n_jobs, int max_params);
+int64_t rcmarl_minibatch_steps(int epochs, int n_times, int mb_times);
+int rcmarl_minibatch_fit(const rcmarl_rows* rows_host, const rcmarl_grad_job* gjobs_host,
+                         const rcmarl_sgd_job* sjobs_host, int n_jobs, int epochs, int n_times, int mb_times,
+                         float lr, void* cells, int64_t cells_bytes, uint32_t seq_first, void* stream);
+
 /* Keras/TF-2 Adam: m,v updated in place, theta -= lr_t*m/(sqrt(v)+eps);
  * g = grad_scale * sums.  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller. */
 typedef struct {
@@ -273,6 +289,9 @@ typedef struct {
     int32_t n_envs, n_agents, n_episodes, max_ep_len;
     int32_t nrow, ncol;
     float gamma, mu;
+    int32_t n_active;           /* agents 0 .. n_active-1 exist (main.py:26 --n_agents); the remaining slots of the
+                                   5- / 16-agent instantiation are written as zeros.  0 means n_agents. */
+    int32_t reserved;
     float state_tab_x[RCMARL_MAX_GRID];   /* (i-mean)/std, rounded from float64 by the host */
     float state_tab_y[RCMARL_MAX_GRID];
 } rcmarl_rollout_args;

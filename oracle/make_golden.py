@@ -18,6 +18,8 @@ container (needs /root/reference, which does not exist on the GPU box).
                            verbatim on seeded inputs with injected fit permutations,
                            plus train_RPBCAC verbatim for 3 cooperative + 1 greedy +
                            1 faulty agent with common_reward=True (2 update rounds).
+6. ref_learning.npz        start weights / task / last-500-episode means of sim_data2.pkl
+                           for the 45 published run directories (tools/learning_harness.py).
 """
 import os
 import re
@@ -385,6 +387,42 @@ def make_adversaries():
     print("adversaries:", len(out), "arrays; train-run perms", len(used))
 
 
+def make_learning_fixture():
+    """Start weights, task and published outcome of every run directory under simulation_results/raw_data (8 scenarios
+    x H in {0,1} x seeds {100,200,300}; 45 exist): the inputs of tools/learning_harness.py and the numbers it prints next
+    to ours (README.md:31-45).  `ref_*` = mean over the last 500 episodes of sim_data2.pkl (run 2 of the published jobs)."""
+    import pandas as pd
+    out, runs = {}, []
+    for scen in sorted(os.listdir(RAW)):
+        for H in (0, 1):
+            for seed in (100, 200, 300):
+                d = os.path.join(RAW, scen, f"H={H}", f"seed={seed}")
+                if not os.path.isdir(d):
+                    continue
+                wfile = "pretrained_weights1.npy" if os.path.exists(os.path.join(d, "pretrained_weights1.npy")) else "pretrained_weights.npy"
+                w = np.load(os.path.join(d, wfile), allow_pickle=True)
+                head = open(os.path.join(d, "out.txt")).read(4000)
+                labels = re.search(r"'agent_label': \[([^\]]*)\]", head).group(1).replace("'", "").replace(" ", "").split(",")
+                common = re.search(r"'common_reward': (\w+)", head).group(1) == "True"
+                dtxt = re.search(r"\}\s*(\[\[.*?\]\])", head, re.S).group(1)
+                desired = np.array([[int(v) for v in row.split()] for row in re.findall(r"\[([\d\s]+)\]", dtxt)], np.int64)
+                df = pd.read_pickle(os.path.join(d, "sim_data2.pkl")).tail(500).mean()
+                tag = f"{scen}/H{H}/s{seed}"
+                runs.append(tag)
+                out[f"{tag}/labels"] = np.array(labels)
+                out[f"{tag}/common_reward"] = np.array(common)
+                out[f"{tag}/desired"] = desired
+                out[f"{tag}/ref_team"] = np.float64(df["True_team_returns"])
+                out[f"{tag}/ref_adv"] = np.float64(df["True_adv_returns"])
+                out[f"{tag}/ref_est"] = np.float64(df["Estimated_team_returns"])
+                for i in range(len(w)):
+                    for k, v in flat_weights(w[i]).items():
+                        out[f"{tag}/agent{i}/{k}"] = v
+    out["runs"] = np.array(runs)
+    np.savez_compressed(os.path.join(OUT, "ref_learning.npz"), **out)
+    print("learning fixture:", len(runs), "runs,", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_kat()
@@ -392,3 +430,4 @@ if __name__ == "__main__":
     make_methods()
     make_train_run()
     make_adversaries()
+    make_learning_fixture()

@@ -84,7 +84,7 @@ class Malicious_CAC_agent(_AdversaryBase):
         if self._critic_local is None:
             return self._critic_local_host
         from rcmarl import nets
-        return nets.unpack(self._critic_local.detach().cpu().numpy(), self.critic.d_in, 1)
+        return nets.unpack_padded(self._critic_local.detach().cpu().numpy(), self.critic.d_in, self.critic.d_in_k, 1)
 
     @critic_local_weights.setter
     def critic_local_weights(self, w):
@@ -96,7 +96,7 @@ class Malicious_CAC_agent(_AdversaryBase):
         if self._critic_local is None:
             import torch
             from rcmarl import nets
-            self._critic_local = torch.as_tensor(nets.pack(self._critic_local_host)).to(self.critic.flat.device)
+            self._critic_local = torch.as_tensor(nets.pack_padded(self._critic_local_host, self.critic.d_in_k)).to(self.critic.flat.device)
         return self._critic_local
 
     def actor_update(self, s, ns, r_local, a_local):                               # :102-119

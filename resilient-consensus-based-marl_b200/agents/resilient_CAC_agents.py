@@ -75,8 +75,8 @@ class RPBCAC_agent():
     # ------------------------------------------------------------------ hidden-layer consensus (:142-166)
     def _hidden(self, model, msgs_innodes):
         dev = model.flat.device
-        stack = torch.stack([A.as_flat(m, dev) for m in msgs_innodes])
-        ops.consensus_hidden([ops.consensus_job(model.flat, stack, stack.shape[1], nets.n_hidden_params(model.d_in),
+        stack = torch.stack([A.as_flat(m, dev, model.d_in_k) for m in msgs_innodes])
+        ops.consensus_hidden([ops.consensus_job(model.flat, stack, stack.shape[1], nets.n_hidden_params(model.d_in_k),
                                                 list(range(len(msgs_innodes))), self.H)])
 
     def resilient_consensus_critic_hidden(self, critic_weights_innodes):
@@ -89,7 +89,7 @@ class RPBCAC_agent():
     def _estimates(self, model, x, msgs_innodes):
         rows, kind, xf = A.rows_for(x, self.n_agents)
         dev = xf.device
-        stack = torch.stack([A.as_flat(m, dev) for m in msgs_innodes])
+        stack = torch.stack([A.as_flat(m, dev, model.d_in_k) for m in msgs_innodes])
         agg = torch.empty(xf.shape[0], dtype=torch.float32, device=dev)
         ops.team(rows, [ops.team_job(model.flat, kind, stack, stack.shape[1], list(range(len(msgs_innodes))), self.H,
                                      agg_out=agg)])

@@ -21,16 +21,19 @@ CommHost* comm_bound() { return g_bound; }
 static size_t data_bytes(const CommHost* c) { return sizeof(uint2) * 2 * (size_t)c->world * (size_t)c->max_floats; }
 static size_t total_bytes(const CommHost* c) { return data_bytes(c) + sizeof(uint32_t) * 8; }
 
-bool comm_next(CommDev* out, int64_t need_floats) {
+bool comm_next(CommDev* out, int64_t need_floats) { return comm_reserve(out, need_floats, 1u); }
+
+bool comm_reserve(CommDev* out, int64_t need_floats, uint32_t count) {
     CommHost* c = g_bound;
-    if (!c || !c->connected || need_floats > c->max_floats) return false;
-    c->seq += 1;
+    if (!c || !c->connected || need_floats > c->max_floats || count < 1) return false;
+    const uint32_t first = c->seq + 1;
+    c->seq += count;
     for (int p = 0; p < COMM_MAX_WORLD; ++p) out->cells[p] = p < c->world ? (uint2*)c->peer_base[p] : nullptr;
     out->error = (uint32_t*)((char*)c->base + data_bytes(c));
     out->max_floats = c->max_floats;
     out->rank = c->rank;
     out->world = c->world;
-    out->seq = c->seq;
+    out->seq = first;
     return true;
 }
 

@@ -40,27 +40,30 @@ __device__ __forceinline__ uint2 ld_cell(const uint2* p) {
 }
 
 // cell of element `offset` from source rank `src` in slot (seq & 1) of a buffer
-__device__ __forceinline__ int64_t comm_index(const CommDev& c, int src, int64_t offset) {
-    return ((int64_t)(c.seq & 1u) * c.world + src) * c.max_floats + offset;
+__device__ __forceinline__ int64_t comm_index(const CommDev& c, int src, int64_t offset, uint32_t seq) {
+    return ((int64_t)(seq & 1u) * c.world + src) * c.max_floats + offset;
 }
 // step 1: push this rank's value of element `offset` to every peer (own buffer included)
-__device__ __forceinline__ void comm_push(const CommDev& c, int64_t offset, float v) {
-    const int64_t idx = comm_index(c, c.rank, offset);
+__device__ __forceinline__ void comm_push(const CommDev& c, int64_t offset, float v, uint32_t seq) {
+    const int64_t idx = comm_index(c, c.rank, offset, seq);
 #pragma unroll
     for (int p = 0; p < COMM_MAX_WORLD; ++p)
-        if (p < c.world) st_cell(c.cells[p] + idx, v, c.seq);
+        if (p < c.world) st_cell(c.cells[p] + idx, v, seq);
 }
 // step 2: wait for element `offset` of every rank in OUR buffer, rank-ordered sum
-__device__ __forceinline__ float comm_wait_total(const CommDev& c, int64_t offset) {
+__device__ __forceinline__ float comm_wait_total(const CommDev& c, int64_t offset, uint32_t seq) {
     float v[COMM_MAX_WORLD];
     const long long t0 = clock64();
+    const uint2* mine = c.cells[0];
+#pragma unroll
+    for (int p = 1; p < COMM_MAX_WORLD; ++p) mine = (p == c.rank) ? c.cells[p] : mine;
 #pragma unroll
     for (int p = 0; p < COMM_MAX_WORLD; ++p) {
         v[p] = 0.f;
         if (p < c.world) {
-            const uint2* cell = c.cells[c.rank] + comm_index(c, p, offset);
+            const uint2* cell = mine + comm_index(c, p, offset, seq);
             uint2 x = ld_cell(cell);
-            while (x.y != c.seq) {
+            while (x.y != seq) {
                 if (clock64() - t0 > 120000000000LL) {   // ~60 s: a peer died; fail loudly instead of hanging the GPU
                     *c.error = 1u;
                     __threadfence_system();
@@ -76,10 +79,13 @@ __device__ __forceinline__ float comm_wait_total(const CommDev& c, int64_t offse
     for (int p = 0; p < COMM_MAX_WORLD; ++p) tot += v[p];   // rank order: identical bits on every rank
     return tot;
 }
+__device__ __forceinline__ void comm_push(const CommDev& c, int64_t offset, float v) { comm_push(c, offset, v, c.seq); }
+__device__ __forceinline__ float comm_wait_total(const CommDev& c, int64_t offset) { return comm_wait_total(c, offset, c.seq); }
 
 // host side (comm.cu)
 struct CommHost;
 CommHost* comm_bound();
 bool comm_next(CommDev* out, int64_t need_floats);   // fills *out with the next sequence number; false if unbound
+bool comm_reserve(CommDev* out, int64_t need_floats, uint32_t count);   // `count` consecutive numbers, out->seq = the first
 
 }  // namespace rcmarl

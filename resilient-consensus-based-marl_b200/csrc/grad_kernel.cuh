@@ -160,49 +160,83 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
-// y / gy: index of this CTA among the gy CTAs of its job
+// GradCore: the per-CTA machinery of the fused forward + backward pass, split into set-up (once per kernel), the row
+// sweep (register accumulators) and the fixed-order CTA reduction, so that the one-shot kernel (grad_kernel) and the
+// persistent mini-batch kernel (minibatch_persist.cuh) share one body.  All members live in registers (everything is
+// force-inlined and fully unrolled).
 template <int NA, int DIN, int NOUT, int GRAD_WARPS>
-__device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad_job& job, float* smem, int y, int gy) {
+struct GradCore {
     using L = TileLayout<DIN, NOUT>;
-    constexpr int NP = param_count(DIN, NOUT);
-    constexpr int R = 2;
-    rcmarl_rows Rw = P.rows;
-    if (job.time_idx) Rw.time_idx = job.time_idx;
-    float* sw = smem;
-    float* tiles = smem + round4(NP);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* wt = tiles + warp * (L::ROWS * L::RS);
-    constexpr int SROW = 3 * NA;                                     // staged row = one sa row (ns rows are shorter)
-    constexpr int SWARP = grad_use_tma(NA) ? L::ROWS * SROW : 0;      // staging floats per warp
-    float* stage = tiles + GRAD_WARPS * (L::ROWS * L::RS) + warp * SWARP;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + GRAD_WARPS * (L::ROWS * L::RS) + GRAD_WARPS * SWARP) + warp;
+    static constexpr int NP = param_count(DIN, NOUT);
+    static constexpr int R = 2;
+    static constexpr int SROW = 3 * NA;                                     // staged row = one sa row (ns rows are shorter)
+    static constexpr int SWARP = grad_use_tma(NA) ? L::ROWS * SROW : 0;      // staging floats per warp
+    static constexpr bool kPadHoist = RCMARL_PAD_HOIST != 0;
 
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    pdl_wait();                       // everything above overlaps the tail of the previous kernel (PDL)
-    stage_weights(sw, job.w, NP);
-    __syncthreads();
-    const SmemW W{sw};
-    constexpr bool kPadHoist = RCMARL_PAD_HOIST != 0;
-    if constexpr (kPadHoist) {
-        // the constant columns of this lane's two tile rows ([.., 1, 0 pad] of the activations, zero pad of the deltas)
-        // never change: write them once instead of once per chunk
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float* rowp = wt + (lane + 32 * r) * L::RS;
-#pragma unroll
-            for (int q = 0; q < L::LA1 / 4; ++q)
-                if (4 * q >= DIN) st4(rowp + L::OA1 + 4 * q, 4 * q == DIN ? 1.f : 0.f, 0.f, 0.f, 0.f);
-            st4(rowp + L::OA2 + 20, 1.f, 0.f, 0.f, 0.f);
-            if constexpr (L::L3T) st4(rowp + L::OA3 + 20, 1.f, 0.f, 0.f, 0.f);
-            st4(rowp + L::OD1 + 20, 0.f, 0.f, 0.f, 0.f);
-            st4(rowp + L::OD2 + 20, 0.f, 0.f, 0.f, 0.f);
+    float* sw;          // staged network parameters (shared)
+    float* tiles;       // [GRAD_WARPS][ROWS][RS]
+    float* wt;          // this warp's tile
+    float* stage;       // this warp's bulk-copy staging buffer
+    uint64_t* bar;      // this warp's mbarrier
+    int warp, lane;
+    uint32_t phase;
+    // phase-2 assignment of this lane: tile `tile`, row group `grp`
+    int grp, aoff, doff;
+    f2 acc[32];                            // 8x8 tile, packed as pairs over the delta index
+    float g3[L::L3T ? 1 : HID + 1];       // scalar nets: output-layer gradient per lane [W3(20) | b3]
+    float loss;
+
+    // shared-memory carve-up + mbarrier init; nothing here touches global memory (may run before pdl_wait)
+    __device__ __forceinline__ void setup(float* smem) {
+        sw = smem;
+        tiles = smem + round4(NP);
+        warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        wt = tiles + warp * (L::ROWS * L::RS);
+        stage = tiles + GRAD_WARPS * (L::ROWS * L::RS) + warp * SWARP;
+        bar = reinterpret_cast<uint64_t*>(tiles + GRAD_WARPS * (L::ROWS * L::RS) + GRAD_WARPS * SWARP) + warp;
+        phase = 0;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncwarp();
+        const bool busy = lane < L::NG * L::NT;
+        const int tile = busy ? lane % L::NT : 0;
+        grp = busy ? lane / L::NT : 0;
+        L::tile_offsets(tile, aoff, doff);
     }
 
+    // the constant columns of this lane's two tile rows ([.., 1, 0 pad] of the activations, zero pad of the deltas)
+    // never change: write them once instead of once per chunk.  Must be repeated after cta_reduce (which reuses the tiles).
+    __device__ __forceinline__ void write_pads() {
+        if constexpr (kPadHoist) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float* rowp = wt + (lane + 32 * r) * L::RS;
+#pragma unroll
+                for (int q = 0; q < L::LA1 / 4; ++q)
+                    if (4 * q >= DIN) st4(rowp + L::OA1 + 4 * q, 4 * q == DIN ? 1.f : 0.f, 0.f, 0.f, 0.f);
+                st4(rowp + L::OA2 + 20, 1.f, 0.f, 0.f, 0.f);
+                if constexpr (L::L3T) st4(rowp + L::OA3 + 20, 1.f, 0.f, 0.f, 0.f);
+                st4(rowp + L::OD1 + 20, 0.f, 0.f, 0.f, 0.f);
+                st4(rowp + L::OD2 + 20, 0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+        }
+    }
+
+    __device__ __forceinline__ void zero_acc() {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = pack2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < (L::L3T ? 1 : HID + 1); ++j) g3[j] = 0.f;
+        loss = 0.f;
+    }
+
+    // Sweep the rows of `Rw` that belong to CTA y of gy (64-row chunks, see below); weights are read from `sw`.
+    // Accumulates into acc / g3 / loss.
+    __device__ __forceinline__ void sweep(const rcmarl_rows& Rw, const rcmarl_grad_job& job, int y, int gy) {
+    const SmemW W{sw};
     // Input staging by the TMA engine: the 64 rows of a chunk are one contiguous, 16-byte aligned span of sa / ns whenever
     // the chunk is full and (contiguous row mode, or gathered mode with n_envs % 64 == 0); lane 0 issues one 1-D bulk copy
     // per chunk, completion is tracked by the warp's mbarrier; other chunks fall back to per-lane loads.
@@ -215,7 +249,6 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
         src = in_base + row_of(Rw, c * L::ROWS) * rowf;
         return (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     };
-    uint32_t phase = 0;
     bool staged = false;
     // Chunk c of the job goes to (CTA y, warp w) with c = k * cstep + w * gy + y (RCMARL_CHUNK_WARP_MAJOR, default) or
     // c = k * cstep + y * GRAD_WARPS + w.  Both cover every chunk exactly once; they differ in who runs the last, partial
@@ -232,23 +265,11 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
         const int64_t c0 = cfirst;
         const float* src = nullptr;
         if (c0 * L::ROWS < Rw.n_rows) staged = stage_src(c0, src);
-        if (staged && lane == 0) bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
+        if (staged && lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of the buffer
+            bulk_load(stage, src, (uint32_t)(L::ROWS * rowf * sizeof(float)), bar);
+        }
     }
-
-    // phase-2 assignment of this lane: tile `tile`, row group `grp`
-    const bool busy = lane < L::NG * L::NT;
-    const int tile = busy ? lane % L::NT : 0;
-    const int grp = busy ? lane / L::NT : 0;
-    int aoff, doff;
-    L::tile_offsets(tile, aoff, doff);
-    f2 acc[32];                            // 8x8 tile, packed as pairs over the delta index
-#pragma unroll
-    for (int e = 0; e < 32; ++e) acc[e] = pack2(0.f, 0.f);
-    float g3[L::L3T ? 1 : HID + 1];       // scalar nets: output-layer gradient per lane [W3(20) | b3]
-#pragma unroll
-    for (int j = 0; j < (L::L3T ? 1 : HID + 1); ++j) g3[j] = 0.f;
-    float loss = 0.f;
-
     const int64_t nchunks = (Rw.n_rows + L::ROWS - 1) / L::ROWS;
     for (int64_t c = cfirst; c < nchunks; c += cstep) {
         // ---------------- phase 1: two rows per lane (lane, lane + 32 of the chunk) ----------------
@@ -418,10 +439,13 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
         __syncwarp();
     }
 
-    // ---------------- CTA reduction (fixed order => bitwise reproducible) ----------------
-#if RCMARL_PDL_REDUCE
-    pdl_launch_dependents();
-#endif
+    }
+
+    // CTA reduction in fixed order (bitwise reproducible): store(i, v) receives this CTA's gradient sums for the packed
+    // parameters i = 0 .. NP-1 and the loss sum as i = NP (each index exactly once, from some thread).
+    // Reuses the tile region (call write_pads() before the next sweep).  All threads must call it.
+    template <class ST>
+    __device__ __forceinline__ void cta_reduce(ST store) {
     __syncthreads();
     float* red = tiles;                               // [GRAD_WARPS][32][64]
     {
@@ -445,7 +469,6 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
         }
     }
     __syncthreads();
-    float* out = P.partial + (int64_t)blockIdx.x * P.stride;
     for (int q = threadIdx.x; q < L::NT * 64; q += blockDim.x) {
         const int t = q >> 6, e = q & 63;
         const int idx = L::tile_param(t, e >> 3, e & 7);
@@ -454,21 +477,42 @@ __device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad
             for (int w = 0; w < GRAD_WARPS; ++w)
 #pragma unroll
                 for (int g = 0; g < L::NG; ++g) s += red[(w * 32 + g * L::NT + t) * 64 + e];
-            out[idx] = s;
+            store(idx, s);
         }
     }
     if constexpr (!L::L3T) {
         if (threadIdx.x <= HID) {
             float s = 0.f;
             for (int w = 0; w < GRAD_WARPS; ++w) s += red3[w * (HID + 2) + threadIdx.x];
-            out[(threadIdx.x < HID ? off_W3(DIN) : off_b3(DIN, 1) - HID) + threadIdx.x] = s;
+            store((threadIdx.x < HID ? off_W3(DIN) : off_b3(DIN, 1) - HID) + threadIdx.x, s);
         }
     }
     if (threadIdx.x == 32) {
         float s = 0.f;
         for (int w = 0; w < GRAD_WARPS; ++w) s += red3[w * (HID + 2) + HID + 1];
-        out[NP] = s;
+        store(NP, s);
     }
+    }
+};
+
+// y / gy: index of this CTA among the gy CTAs of its job
+template <int NA, int DIN, int NOUT, int GRAD_WARPS>
+__device__ __forceinline__ void grad_body(const GradParams& P, const rcmarl_grad_job& job, float* smem, int y, int gy) {
+    GradCore<NA, DIN, NOUT, GRAD_WARPS> core;
+    rcmarl_rows Rw = P.rows;
+    if (job.time_idx) Rw.time_idx = job.time_idx;
+    core.setup(smem);
+    pdl_wait();                       // everything above overlaps the tail of the previous kernel (PDL)
+    stage_weights(core.sw, job.w, core.NP);
+    __syncthreads();
+    core.write_pads();
+    core.zero_acc();
+    core.sweep(Rw, job, y, gy);
+#if RCMARL_PDL_REDUCE
+    pdl_launch_dependents();
+#endif
+    float* out = P.partial + (int64_t)blockIdx.x * P.stride;
+    core.cta_reduce([out](int i, float v) { out[i] = v; });
 }
 
 template <int NA, int LOSS>

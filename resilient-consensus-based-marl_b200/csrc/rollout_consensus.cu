@@ -294,14 +294,20 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ rc
     const uint64_t gep = (uint64_t)(A.episode_offset + ep);
     const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
     const float one_minus_mu = 1.0f - A.mu;
+    // agents nact .. NA-1 are unused slots of the instantiation (a team smaller than NA): they do not act, and their
+    // state / action / reward columns are written as zeros (rcmarl/nets.py: the padded problem is the nact-agent problem)
+    const int nact = (A.n_active > 0 && A.n_active < NA) ? A.n_active : NA;
 
     int px[NA], py[NA], gx[NA], gy[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
         gx[i] = A.desired[2 * i];
         gy[i] = A.desired[2 * i + 1];
-        if (A.init_state) {                                        // env.reset(), grid_world.py:37-45
-            const int32_t* s0 = A.init_state + (((int64_t)ep * A.n_envs + env) * NA + i) * 2;
+        if (i >= nact) {
+            px[i] = 0;
+            py[i] = 0;
+        } else if (A.init_state) {                                 // env.reset(), grid_world.py:37-45
+            const int32_t* s0 = A.init_state + (((int64_t)ep * A.n_envs + env) * nact + i) * 2;
             px[i] = s0[0];
             py[i] = s0[1];
         } else {
@@ -313,7 +319,10 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ rc
     }
     float x[DIN];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) { x[2 * i] = A.state_tab_x[px[i]]; x[2 * i + 1] = A.state_tab_y[py[i]]; }
+    for (int i = 0; i < NA; ++i) {
+        x[2 * i] = i < nact ? A.state_tab_x[px[i]] : 0.f;
+        x[2 * i + 1] = i < nact ? A.state_tab_y[py[i]] : 0.f;
+    }
 
     float* est = A.est + ((int64_t)ep * A.n_envs + env) * NA;
     float* retp = A.ret + ((int64_t)ep * A.n_envs + env) * NA;
@@ -321,6 +330,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ rc
 #pragma unroll 1
     for (int i = 0; i < NA; ++i) {                                 // train_agents.py:60-62
         float h1[HID], h2[HID];
+        if (i >= nact) { est[i] = 0.f; continue; }
         features<DIN>(sc_w + i * PCr, x, h1, h2);
         est[i] = head1<DIN>(sc_w + i * PCr, h2);
     }
@@ -337,12 +347,13 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ rc
 #pragma unroll 1
         for (int i = 0; i < NA; ++i) {
             float h1[HID], h2[HID], p[NACT], mx, lse;
+            if (i >= nact) { act[i] = 0; continue; }
             features<DIN>(sa_w + i * PAr, x, h1, h2);
             head5<DIN>(sa_w + i * PAr, h2, p);
             softmax5(p, mx, lse);
             float u0, u1, u2;
             if (A.uniforms) {
-                const float* u = A.uniforms + ((((int64_t)ep * A.max_ep_len + j) * A.n_envs + env) * NA + i) * 3;
+                const float* u = A.uniforms + ((((int64_t)ep * A.max_ep_len + j) * A.n_envs + env) * nact + i) * 3;
                 u0 = u[0]; u1 = u[1]; u2 = u[2];
             } else {
                 const uint4 rnd = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)gep,
@@ -359,9 +370,10 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ rc
         }
 #pragma unroll
         for (int i = 0; i < NA; ++i) {                             // env.step + get_data
-            const float rew = agent_step(px[i], py[i], act[i], gx[i], gy[i], A.nrow);
-            x[2 * i] = A.state_tab_x[px[i]];
-            x[2 * i + 1] = A.state_tab_y[py[i]];
+            float rew = agent_step(px[i], py[i], act[i], gx[i], gy[i], A.nrow);
+            x[2 * i] = i < nact ? A.state_tab_x[px[i]] : 0.f;
+            x[2 * i + 1] = i < nact ? A.state_tab_y[py[i]] : 0.f;
+            rew = i < nact ? rew : 0.f;
             ns[2 * i] = x[2 * i];
             ns[2 * i + 1] = x[2 * i + 1];
             rr[i] = rew;

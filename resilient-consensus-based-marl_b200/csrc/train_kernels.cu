@@ -37,6 +37,7 @@
 #include "grad_kernel_tc.cuh"
 #endif
 #include "comm.cuh"
+#include "minibatch_persist.cuh"
 
 namespace rcmarl {
 
@@ -637,6 +638,34 @@ static int grad_job_cost(int na, int kind, int loss_mode) {
     return grad_row_cost(kind == RCMARL_IN_SA ? 3 * na : 2 * na, 1);
 }
 
+template <int NA>
+static int launch_mb_persist(const MbParams& P, int n_ctas, cudaStream_t st) {
+    constexpr int NW = grad_warps<NA, RCMARL_LOSS_MSE>();
+    constexpr size_t smem = sizeof(float) * (grad_smem_floats<NA, 3 * NA, 1, NW>() > grad_smem_floats<NA, 2 * NA, 1, NW>()
+                                                 ? grad_smem_floats<NA, 3 * NA, 1, NW>() : grad_smem_floats<NA, 2 * NA, 1, NW>());
+    static int resident = -1;                          // CTAs that can be co-resident (the cells protocol needs all of them)
+    if (resident < 0) {
+        if (set_smem(mb_persist_kernel<NA>, smem)) return RCMARL_ERR_CUDA;
+        int per_sm = 0;
+        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_persist_kernel<NA>, 32 * NW, smem));
+        resident = per_sm * sm_count_cached();
+    }
+    if (n_ctas > resident) return RCMARL_ERR_ARG;
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(32 * NW);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = &pdl;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, mb_persist_kernel<NA>, P));
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace rcmarl
 
 using namespace rcmarl;
@@ -799,6 +828,74 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
         }
     }
     return RCMARL_OK;
+}
+
+int64_t rcmarl_minibatch_cells_bytes(int n_jobs, int max_params) {
+    if (n_jobs < 1) n_jobs = 1;
+    // level 1: one row of cells per CTA (<= SMs); level 2 (single GPU): 2 slots x n_jobs rows; + the error word
+    return ((int64_t)sm_count_cached() + 2 * (int64_t)n_jobs) * (int64_t)(max_params + 1) * (int64_t)sizeof(uint2) + 64;
+}
+
+int64_t rcmarl_minibatch_steps(int epochs, int n_times, int mb_times) {
+    if (epochs < 1 || n_times < 1 || mb_times < 1) return 0;
+    return (int64_t)epochs * ((n_times + mb_times - 1) / mb_times);
+}
+
+int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, const rcmarl_sgd_job* sjobs, int n_jobs,
+                         int epochs, int n_times, int mb_times, float lr, void* cells, int64_t cells_bytes,
+                         uint32_t seq_first, void* stream) {
+    if (!rows || !rows->sa || !rows->ns || !rows->r || rows->n_envs <= 0) return RCMARL_ERR_ARG;
+    if (rows->n_agents != 5 && rows->n_agents != 16) return RCMARL_ERR_ARG;
+    if (!gjobs || !sjobs || n_jobs < 1 || n_jobs > RCMARL_MAX_JOBS || !cells || epochs < 1 || n_times < 1 || mb_times < 1 ||
+        seq_first < 1)
+        return RCMARL_ERR_ARG;
+    const int NA = rows->n_agents;
+    MbParams P;
+    P.rows = *rows;
+    P.rows.n_rows = 0;
+    P.rows.time_idx = nullptr;
+    int maxn = 0;
+    int cost[RCMARL_MAX_JOBS];
+    for (int j = 0; j < n_jobs; ++j) {
+        const rcmarl_grad_job& q = gjobs[j];
+        if (!q.w || !q.target || !q.time_idx || q.kind < 0 || q.kind > 2 || q.target_stride < 1) return RCMARL_ERR_ARG;
+        if (!sjobs[j].dst || sjobs[j].dst != sjobs[j].src || (const float*)sjobs[j].dst != q.w) return RCMARL_ERR_ARG;
+        const int n = param_count(q.kind == RCMARL_IN_SA ? 3 * NA : 2 * NA, 1);
+        if (sjobs[j].n != n || sjobs[j].first != 0) return RCMARL_ERR_ARG;
+        MbChain& c = P.chains[j];
+        c.w = sjobs[j].dst; c.target = q.target; c.time_idx = q.time_idx; c.loss_out = sjobs[j].loss_out;
+        c.target_stride = q.target_stride; c.lr = sjobs[j].coef > 0.f ? sjobs[j].coef : lr;
+        c.loss_coef = sjobs[j].loss_coef; c.kind = q.kind; c.loss_accumulate = sjobs[j].loss_accumulate;
+        cost[j] = grad_job_cost(NA, q.kind, RCMARL_LOSS_MSE);
+        if (n + 1 > maxn) maxn = n + 1;
+    }
+    // CTA shares by cost (the chains do not share rows in L2 the way the lock-step full-batch jobs do)
+    const int cpc = NA == 5 ? grad_chunks_per_cta<5>(RCMARL_LOSS_MSE) : grad_chunks_per_cta<16>(RCMARL_LOSS_MSE);
+    const int64_t n_rows_mb = (int64_t)(n_times < mb_times ? n_times : mb_times) * rows->n_envs;
+    int g[RCMARL_MAX_JOBS];
+    plan_shares(n_jobs, cost, (n_rows_mb + 63) / 64, cpc, sm_count_cached(), true, g);
+    int n_ctas = 0;
+    for (int j = 0; j < n_jobs; ++j) { P.cta_first[j] = (int16_t)n_ctas; n_ctas += g[j]; }
+    P.cta_first[n_jobs] = (int16_t)n_ctas;
+    P.n_chains = n_jobs; P.epochs = epochs; P.n_times = n_times; P.mb_times = mb_times; P.stride = maxn;
+    const int64_t steps = rcmarl_minibatch_steps(epochs, n_times, mb_times);
+    if ((uint64_t)seq_first + (uint64_t)steps >= 0xFFFFFFFFull) return RCMARL_ERR_ARG;
+    const int64_t l1 = (int64_t)n_ctas * maxn, l2 = 2 * (int64_t)n_jobs * maxn;
+    if ((l1 + l2) * (int64_t)sizeof(uint2) + 64 > cells_bytes) return RCMARL_ERR_WORKSPACE;
+    if (((uintptr_t)cells & 15) != 0) return RCMARL_ERR_ARG;
+    P.cells1 = (uint2*)cells;
+    P.seq1 = seq_first;
+    if (comm_bound()) {
+        if (!comm_reserve(&P.comm, (int64_t)n_jobs * maxn, (uint32_t)steps)) return RCMARL_ERR_ARG;
+    } else {
+        for (int p = 0; p < COMM_MAX_WORLD; ++p) P.comm.cells[p] = nullptr;
+        P.comm.cells[0] = (uint2*)cells + l1;
+        P.comm.error = (uint32_t*)((uint2*)cells + l1 + l2);
+        P.comm.max_floats = (int64_t)n_jobs * maxn;
+        P.comm.rank = 0; P.comm.world = 1; P.comm.seq = seq_first;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    return NA == 5 ? launch_mb_persist<5>(P, n_ctas, st) : launch_mb_persist<16>(P, n_ctas, st);
 }
 
 int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs, void* ws, int64_t ws_bytes,

@@ -69,6 +69,7 @@ class RolloutArgs(C.Structure):
                 ("seed", C.c_uint64), ("env_offset", C.c_int64), ("episode_offset", C.c_int64),
                 ("n_envs", C.c_int32), ("n_agents", C.c_int32), ("n_episodes", C.c_int32), ("max_ep_len", C.c_int32),
                 ("nrow", C.c_int32), ("ncol", C.c_int32), ("gamma", C.c_float), ("mu", C.c_float),
+                ("n_active", C.c_int32), ("reserved", C.c_int32),
                 ("state_tab_x", C.c_float * MAX_GRID), ("state_tab_y", C.c_float * MAX_GRID)]
 
 
@@ -90,6 +91,10 @@ SYMBOLS = [
     ("rcmarl_adam_apply", C.c_int, [C.POINTER(AdamJob), C.c_int, c_fp]),
     ("rcmarl_minibatch_sgd", C.c_int, [C.POINTER(Rows), C.POINTER(GradJob), C.POINTER(SgdJob), C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_float, c_fp, C.c_int64, c_fp]),
+    ("rcmarl_minibatch_cells_bytes", C.c_int64, [C.c_int, C.c_int]),
+    ("rcmarl_minibatch_steps", C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    ("rcmarl_minibatch_fit", C.c_int, [C.POINTER(Rows), C.POINTER(GradJob), C.POINTER(SgdJob), C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_float, c_fp, C.c_int64, C.c_uint32, c_fp]),
     ("rcmarl_team", C.c_int, [C.POINTER(Rows), C.POINTER(TeamJob), C.c_int, c_fp, C.c_int64, c_fp]),
     ("rcmarl_reward_mix", C.c_int, [c_fp, C.c_int64, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_float, c_fp, c_fp]),
     ("rcmarl_comm_create", C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -119,7 +124,10 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the RPBCAC kernels)")
         l = C.CDLL(LIB_PATH)
+        lax = os.environ.get("RCMARL_LIB_LAX") == "1"      # kernel A/B runs against older builds only (tools/ab_grad.py)
         for name, res, args in SYMBOLS:
+            if lax and not hasattr(l, name):
+                continue
             f = getattr(l, name)          # AttributeError if the ABI and the header diverge
             f.restype = res
             f.argtypes = args

@@ -13,14 +13,17 @@ class DeviceWeights(list):
     129-130) and carries the packed device copy the kernels read."""
 
     def __init__(self, flat, d_in, n_out):
-        super().__init__(nets.unpack(flat.detach().cpu().numpy(), d_in, n_out))
+        d_in_k = (flat.numel() - (L.HIDDEN + L.HIDDEN * L.HIDDEN + L.HIDDEN + L.HIDDEN * n_out + n_out)) // L.HIDDEN
+        super().__init__(nets.unpack_padded(flat.detach().cpu().numpy(), d_in, d_in_k, n_out))
         self.flat, self.d_in, self.n_out = flat, d_in, n_out
 
 
-def as_flat(msg, device):
+def as_flat(msg, device, d_in_k=None):
     if hasattr(msg, "flat"):
         return msg.flat
-    return torch.as_tensor(nets.pack(msg)).to(device)
+    if d_in_k is None:
+        return torch.as_tensor(nets.pack(msg)).to(device)
+    return torch.as_tensor(nets.pack_padded(msg, d_in_k)).to(device)
 
 
 def rows_for(x, n_agents):
@@ -29,10 +32,13 @@ def rows_for(x, n_agents):
     x = ops.dev_f32(x)
     B = x.shape[0]
     x = x.reshape(B, -1)
+    nk = nets.kernel_agents(n_agents)                       # kernel instantiation; extra agent slots stay zero
     if x.shape[1] == 3 * n_agents:
-        return ops.make_rows(x, None, None, n_agents), L.IN_SA, x
+        x = nets.pad_agent_slots(x, n_agents, nk)
+        return ops.make_rows(x, None, None, nk), L.IN_SA, x
     if x.shape[1] == 2 * n_agents:
-        return ops.make_rows(None, x, None, n_agents), L.IN_NS, x
+        x = nets.pad_agent_slots(x, n_agents, nk)
+        return ops.make_rows(None, x, None, nk), L.IN_NS, x
     raise ValueError(f"unexpected feature count {x.shape[1]} for {n_agents} agents")
 
 
@@ -103,8 +109,8 @@ def _sa_with_action(s, a_local, n_agents):
     own action column separately, so it is placed in slot 0 of a temporary sa layout (pure data movement)."""
     s = ops.dev_f32(s)
     B = s.shape[0]
-    sa = torch.zeros(B, n_agents, 3, dtype=torch.float32, device=s.device)
-    sa[:, :, :2] = s.reshape(B, n_agents, 2)
+    sa = torch.zeros(B, nets.kernel_agents(n_agents), 3, dtype=torch.float32, device=s.device)
+    sa[:, :n_agents, :2] = s.reshape(B, n_agents, 2)
     sa[:, 0, 2] = col(a_local)
     return sa.reshape(B, -1)
 
@@ -113,7 +119,7 @@ def actor_step(actor_w, adam, s, a_local, delta, n_agents):
     """actor.train_on_batch(s, a_local, sample_weight=delta) (agents/resilient_CAC_agents.py:99)."""
     sa = _sa_with_action(s, a_local, n_agents)
     B, n = sa.shape[0], actor_w.numel()
-    rows = ops.make_rows(sa, None, None, n_agents)
+    rows = ops.make_rows(sa, None, None, nets.kernel_agents(n_agents))
     adam.ensure(actor_w)
     sums = torch.empty(n + 1, dtype=torch.float32, device=actor_w.device)
     loss = torch.zeros(1, dtype=torch.float32, device=actor_w.device)
@@ -129,7 +135,7 @@ def actor_fit_minibatch(actor_w, adam, s, a_local, delta, n_agents, mb_times, pe
     sa = _sa_with_action(s, a_local, n_agents)
     B, n = sa.shape[0], actor_w.numel()
     T = B // n_envs
-    rows = ops.make_rows(sa, None, None, n_agents, time_idx=perm, n_envs=n_envs)
+    rows = ops.make_rows(sa, None, None, nets.kernel_agents(n_agents), time_idx=perm, n_envs=n_envs)
     adam.ensure(actor_w)
     sums = torch.empty(n + 1, dtype=torch.float32, device=actor_w.device)
     loss = torch.zeros(1, dtype=torch.float32, device=actor_w.device)

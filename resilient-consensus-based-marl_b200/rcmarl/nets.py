@@ -25,6 +25,53 @@ def unpack(flat, d_in, n_out):
     return out
 
 
+# ---- agent counts other than the two kernel instantiations (main.py:26 takes any --n_agents) ------------------------------
+# The kernels are instantiated for 5 and 16 agents.  A team of n agents runs on the next instantiation with the extra
+# agent slots ZERO: zero input columns and zero rows of W1.  Forward values are unchanged (0 * w adds exactly 0), the
+# gradient of a padded W1 row is sum(x_pad * delta) = 0, so SGD / Adam / consensus keep those rows at zero: the padded
+# problem is the n-agent problem bit for bit, not an approximation.
+KERNEL_AGENTS = (5, 16)
+
+
+def kernel_agents(n_agents):
+    """Smallest kernel instantiation that holds `n_agents` agents."""
+    for k in KERNEL_AGENTS:
+        if n_agents <= k:
+            return k
+    raise ValueError(f"n_agents = {n_agents} exceeds the largest kernel instantiation ({KERNEL_AGENTS[-1]})")
+
+
+def pack_padded(weights, d_in_k):
+    """list of 6 arrays with W1 of shape (d_in, 20), d_in <= d_in_k -> packed vector of the d_in_k-input network."""
+    w = [np.asarray(a, np.float32) for a in weights]
+    d_in = w[0].shape[0]
+    if d_in == d_in_k:
+        return pack(w)
+    assert d_in < d_in_k
+    W1 = np.zeros((d_in_k, HIDDEN), np.float32)
+    W1[:d_in] = w[0]
+    return pack([W1] + w[1:])
+
+
+def unpack_padded(flat, d_in, d_in_k, n_out):
+    """Inverse of pack_padded: the first d_in rows of W1 and the other five arrays."""
+    w = unpack(flat, d_in_k, n_out)
+    w[0] = w[0][:d_in].copy()
+    return w
+
+
+def pad_agent_slots(x, n_agents, n_kernel):
+    """(B, n_agents, f) or (B, n_agents * f) torch tensor -> (B, n_kernel * f) with zero slots for the extra agents."""
+    import torch
+    B = x.shape[0]
+    x = x.reshape(B, n_agents, -1)
+    if n_agents == n_kernel:
+        return x.reshape(B, -1).contiguous()
+    out = torch.zeros(B, n_kernel, x.shape[2], dtype=x.dtype, device=x.device)
+    out[:, :n_agents] = x
+    return out.reshape(B, -1)
+
+
 def n_hidden_params(d_in):
     """W1, b1, W2, b2 -- the arrays the hidden-layer consensus overwrites
     (agents/resilient_CAC_agents.py:153 `weights_agg[:-2]`)."""

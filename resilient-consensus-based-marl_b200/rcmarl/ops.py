@@ -149,6 +149,32 @@ def minibatch_sgd(rows, gjobs, sjobs, epochs, n_times, mb_times, lr, ws=None):
                                          ws.numel(), _stream()), "rcmarl_minibatch_sgd")
 
 
+class MinibatchCells:
+    """Scratch of the persistent mini-batch kernel (rcmarl_minibatch_fit): zero-initialised {value, sequence} cells plus
+    the host-side sequence counter (every step of every call consumes one number, never reused)."""
+
+    def __init__(self, n_jobs=L.MAX_JOBS, max_params=None, device=None):
+        if max_params is None:
+            max_params = L.param_count(48, 1)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.buf = torch.zeros(L.lib().rcmarl_minibatch_cells_bytes(n_jobs, max_params), dtype=torch.uint8, device=dev)
+        self.seq = 1
+
+
+def minibatch_fit(rows, gjobs, sjobs, epochs, n_times, mb_times, lr, cells):
+    """Whole mini-batch fit (all epochs, all steps, all chains) as ONE persistent kernel (csrc/minibatch_persist.cuh)."""
+    ga = gjobs if isinstance(gjobs, C.Array) else _arr(L.GradJob, gjobs)
+    sa = sjobs if isinstance(sjobs, C.Array) else _arr(L.SgdJob, sjobs)
+    steps = L.lib().rcmarl_minibatch_steps(epochs, n_times, mb_times)
+    if cells.seq + steps >= 0xFFFF0000:                       # 32-bit sequence numbers: start over on clean cells
+        cells.buf.zero_()
+        cells.seq = 1
+    L.check(L.lib().rcmarl_minibatch_fit(C.byref(rows), ga, sa, len(ga), epochs, n_times, mb_times, lr,
+                                         cells.buf.data_ptr(), cells.buf.numel(), cells.seq, _stream()),
+            "rcmarl_minibatch_fit")
+    cells.seq += steps
+
+
 def adam_job(theta, m, v, sums, n, grad_scale, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, loss_out=None, loss_coef=0.0,
              loss_accumulate=0):
     j = L.AdamJob()
@@ -230,7 +256,7 @@ def state_tables(nrow, ncol, scaling=True):
 
 def rollout(actor_w, critic_w, desired, sa, ns, r, time_begin, est, ret, *, n_envs, n_agents, n_episodes, max_ep_len,
             nrow, ncol, gamma, mu=0.1, seed=0, env_offset=0, episode_offset=0, uniforms=None, init_state=None,
-            scaling=True):
+            scaling=True, n_active=None):
     A = L.RolloutArgs()
     A.actor_w, A.critic_w, A.desired = actor_w.data_ptr(), critic_w.data_ptr(), desired.data_ptr()
     A.sa, A.ns, A.r = sa.data_ptr(), ns.data_ptr(), r.data_ptr()
@@ -240,6 +266,7 @@ def rollout(actor_w, critic_w, desired, sa, ns, r, time_begin, est, ret, *, n_en
     A.seed, A.env_offset, A.episode_offset = int(seed), int(env_offset), int(episode_offset)
     A.n_envs, A.n_agents, A.n_episodes, A.max_ep_len = n_envs, n_agents, n_episodes, max_ep_len
     A.nrow, A.ncol, A.gamma, A.mu = nrow, ncol, gamma, mu
+    A.n_active = n_agents if n_active is None else int(n_active)
     if max(nrow, ncol) > L.MAX_GRID:
         raise L.RcmarlError(f"grid {nrow}x{ncol} exceeds RCMARL_MAX_GRID = {L.MAX_GRID}")
     tx, ty = state_tables(nrow, ncol, scaling)

@@ -20,6 +20,7 @@ from . import _lib as L
 from . import dist_util, nets, ops
 
 COOP, GREEDY, MALICIOUS, FAULTY = "Cooperative", "Greedy", "Malicious", "Faulty"
+PAD = "(unused agent slot)"
 
 
 class Trainer:
@@ -29,14 +30,25 @@ class Trainer:
                  perm_source=None, local_steps=5, mb_epochs=10, mb_times=32, actor_mb_times=200,
                  capacity_times=None, adam_state=None, scaling=True, fixed_initial_state=None):
         L.lib()
-        self.labels = list(labels)
-        self.NA = NA = len(self.labels)
-        if NA not in (5, 16):
-            raise L.RcmarlError(f"kernels are instantiated for 5 or 16 agents, got {NA}")
+        # Any team size up to 16 (main.py:26): the kernels are instantiated for 5 and 16 agents, a team of n_real agents
+        # runs on the next instantiation with the extra agent slots zero (inputs and W1 rows, rcmarl/nets.py) -- exactly the
+        # n_real-agent problem.  self.NA is the kernel instantiation, self.n_real the team.
+        self.n_real = len(labels)
+        try:
+            NA = nets.kernel_agents(self.n_real)
+        except ValueError as ex:
+            raise L.RcmarlError(str(ex))
+        self.NA = NA
+        self.labels = list(labels) + [PAD] * (NA - self.n_real)
         self.in_nodes = [list(x) for x in in_nodes]
         self.coop = [i for i, l in enumerate(self.labels) if l == COOP]
         self.N, self.nrow, self.ncol = int(n_envs), int(nrow), int(ncol)
-        self.gamma, self.H, self.fast_lr, self.mu = float(gamma), int(H), float(fast_lr), float(mu)
+        self.gamma, self.mu = float(gamma), float(mu)
+        # per-agent trimming parameter H and fast learning rate (agents/resilient_CAC_agents.py:28-36 stores both per agent)
+        self.H = [int(H)] * NA if np.isscalar(H) else [int(x) for x in H]
+        self.fast_lr = [float(fast_lr)] * NA if np.isscalar(fast_lr) else [float(x) for x in fast_lr]
+        if len(self.H) != NA or len(self.fast_lr) != NA:
+            raise L.RcmarlError("H / fast_lr must be scalars or one value per agent")
         self.slow_lr = [float(slow_lr)] * NA if np.isscalar(slow_lr) else [float(x) for x in slow_lr]
         self.max_ep_len, self.n_ep_fixed, self.n_epochs = int(max_ep_len), int(n_ep_fixed), int(n_epochs)
         self.block = self.max_ep_len * self.n_ep_fixed                    # time rows per fixed-policy block
@@ -62,10 +74,10 @@ class Trainer:
         self.tr = torch.zeros(NA, self.PT, **f32)
         self.critic_local = torch.zeros(NA, self.PC, **f32)
         for i, w in enumerate(weights):
-            self.actor[i].copy_(torch.as_tensor(nets.pack(w[0])))
-            self.critic[i].copy_(torch.as_tensor(nets.pack(w[1])))
-            self.tr[i].copy_(torch.as_tensor(nets.pack(w[2])))
-            self.critic_local[i].copy_(torch.as_tensor(nets.pack(w[3] if len(w) > 3 else w[1])))
+            self.actor[i].copy_(torch.as_tensor(nets.pack_padded(w[0], 2 * NA)))
+            self.critic[i].copy_(torch.as_tensor(nets.pack_padded(w[1], 2 * NA)))
+            self.tr[i].copy_(torch.as_tensor(nets.pack_padded(w[2], 3 * NA)))
+            self.critic_local[i].copy_(torch.as_tensor(nets.pack_padded(w[3] if len(w) > 3 else w[1], 2 * NA)))
         self.msg_c = torch.zeros(NA, self.PC, **f32)
         self.msg_t = torch.zeros(NA, self.PT, **f32)
         self.adam_m = torch.zeros(NA, self.PA, **f32)
@@ -75,7 +87,9 @@ class Trainer:
             for i, st in enumerate(adam_state):
                 if st is not None:
                     self.adam_m[i].copy_(st[0]); self.adam_v[i].copy_(st[1]); self.adam_t[i] = int(st[2])
-        self.desired = torch.as_tensor(np.asarray(desired, np.int32).reshape(NA, 2)).to(self.dev)
+        des = np.zeros((NA, 2), np.int32)
+        des[:self.n_real] = np.asarray(desired, np.int32).reshape(self.n_real, 2)
+        self.desired = torch.as_tensor(des).to(self.dev)
 
         # replay buffer (time-major, row = t * N + e); capacity = buffer_size + one block
         self.Tcap = int(capacity_times) if capacity_times else self.buffer_size + self.block
@@ -100,6 +114,10 @@ class Trainer:
         self.loss_t = torch.zeros(NA, **f32)
         self.loss_a = torch.zeros(NA, **f32)
         self.ws = ops.workspace(L.MAX_JOBS, self.PT if NA == 5 else L.param_count(48, 1))
+        # persistent mini-batch kernel (rcmarl_minibatch_fit); RCMARL_MB_PERSIST=0 selects the round-1 launch chain
+        self.mb_cells = None
+        if os.environ.get("RCMARL_MB_PERSIST", "1") != "0":
+            self.mb_cells = ops.MinibatchCells(L.MAX_JOBS, self.PT if NA == 5 else L.param_count(48, 1), self.dev)
         self.launches = 0                                 # kernels launched by this engine (bench: gpu_launches)
         self.profile = None                               # bench.py: {"fit_grad": [(start_evt, end_evt), ...], ...}
         self.h2d_bytes = 4 * sum(x.numel() for x in (self.actor, self.critic, self.tr, self.critic_local))
@@ -159,12 +177,13 @@ class Trainer:
 
     def get_weights(self, i):
         """[actor, critic, TR(, critic_local)] as Keras weight lists (get_parameters, res..py:221-223)."""
-        NA = self.NA
+        NA, n = self.NA, self.n_real
         self.d2h_bytes += 4 * (self.PA + self.PC + self.PT + (self.PC if self.labels[i] == MALICIOUS else 0))
-        out = [nets.unpack(self.actor[i].cpu().numpy(), 2 * NA, 5), nets.unpack(self.critic[i].cpu().numpy(), 2 * NA, 1),
-               nets.unpack(self.tr[i].cpu().numpy(), 3 * NA, 1)]
+        out = [nets.unpack_padded(self.actor[i].cpu().numpy(), 2 * n, 2 * NA, 5),
+               nets.unpack_padded(self.critic[i].cpu().numpy(), 2 * n, 2 * NA, 1),
+               nets.unpack_padded(self.tr[i].cpu().numpy(), 3 * n, 3 * NA, 1)]
         if self.labels[i] == MALICIOUS:
-            out.append(nets.unpack(self.critic_local[i].cpu().numpy(), 2 * NA, 1))
+            out.append(nets.unpack_padded(self.critic_local[i].cpu().numpy(), 2 * n, 2 * NA, 1))
         return out
 
     # ------------------------------------------------------------------ rollout
@@ -186,7 +205,7 @@ class Trainer:
         if self.world > 1:
             dist_util.allreduce_sums(stats, self.world, self.group)     # logging only (NCCL)
             stats /= self.world
-        stats = stats.cpu().numpy()
+        stats = stats.cpu().numpy()[:, :, :self.n_real]
         self.d2h_bytes += stats.nbytes
         return stats[0], stats[1]
 
@@ -199,7 +218,7 @@ class Trainer:
             init_state = self._fixed_init_dev
         ops.rollout(self.actor, self.critic, self.desired, self.sa, self.ns, self.r, self.t_filled, est, ret,
                     n_envs=self.N, n_agents=self.NA, n_episodes=n_ep, max_ep_len=Lq, nrow=self.nrow, ncol=self.ncol,
-                    gamma=self.gamma, mu=self.mu, seed=self.seed, env_offset=self.rank * self.N,
+                    n_active=self.n_real, gamma=self.gamma, mu=self.mu, seed=self.seed, env_offset=self.rank * self.N,
                     episode_offset=self.episodes_done, uniforms=uniforms, init_state=init_state, scaling=self.scaling)
 
     def load_rows(self, s, ns, a, r):
@@ -207,20 +226,22 @@ class Trainer:
         s, ns: (B, NA, 2); a, r: (B, NA, 1) as lists / NumPy arrays / (pinned) host or device torch tensors;
         B must be a multiple of n_envs, rows time-major.  The sa = concat([s, a]) of train_agents.py:93 is formed by
         strided device copies (data movement only)."""
+        n = self.n_real
+
         def t(x, last):
             if not isinstance(x, torch.Tensor):
                 x = torch.as_tensor(np.asarray(x, np.float32))
-            return x.reshape(-1, self.NA, last)
+            return x.reshape(-1, n, last)
         s, ns, a, r = t(s, 2), t(ns, 2), t(a, 1), t(r, 1)
         B = s.shape[0]
         assert B % self.N == 0 and self.t_filled * self.N + B <= self.Tcap * self.N
         o = self.t_filled * self.N
-        sa3 = self.sa.view(-1, self.NA, 3)
-        sa3[o:o + B, :, :2].copy_(s.to(self.dev, dtype=torch.float32, non_blocking=True))
-        sa3[o:o + B, :, 2:].copy_(a.to(self.dev, dtype=torch.float32, non_blocking=True))
-        self.ns.view(-1, self.NA, 2)[o:o + B].copy_(ns.to(self.dev, dtype=torch.float32, non_blocking=True))
-        self.r.view(-1, self.NA, 1)[o:o + B].copy_(r.to(self.dev, dtype=torch.float32, non_blocking=True))
-        self.h2d_bytes += 4 * B * self.NA * 6
+        sa3 = self.sa.view(-1, self.NA, 3)                      # unused agent slots stay zero (the buffers start zeroed)
+        sa3[o:o + B, :n, :2].copy_(s.to(self.dev, dtype=torch.float32, non_blocking=True))
+        sa3[o:o + B, :n, 2:].copy_(a.to(self.dev, dtype=torch.float32, non_blocking=True))
+        self.ns.view(-1, self.NA, 2)[o:o + B, :n].copy_(ns.to(self.dev, dtype=torch.float32, non_blocking=True))
+        self.r.view(-1, self.NA, 1)[o:o + B, :n].copy_(r.to(self.dev, dtype=torch.float32, non_blocking=True))
+        self.h2d_bytes += 4 * B * n * 6
         self.t_filled += B // self.N
 
     # ------------------------------------------------------------------ update round
@@ -262,8 +283,8 @@ class Trainer:
         td_arr = (L.ValueJob * len(td_jobs))(*td_jobs) if td_jobs else None
 
         fit_first, fit_next, fit_apply_first, fit_apply_next = [], [], [], []
-        lr2 = self.fast_lr * 2.0 / Bg
         for n, i in enumerate(coop):
+            lr2 = self.fast_lr[i] * 2.0 / Bg
             tgt_t, st_t = applied(i)
             sc, stt = self.sums_fit[2 * n][:self.PC + 1], self.sums_fit[2 * n + 1]
             for first in (True, False):
@@ -282,24 +303,25 @@ class Trainer:
         fit_apply_first, fit_apply_next = arr(L.SgdJob, fit_apply_first), arr(L.SgdJob, fit_apply_next)
 
         # mini-batch chains of the adversaries (adversarial:133,150,163,239,251), node order = permutation order
-        chains = []                                       # (weights in place, kind, target, stride, loss slot)
+        chains = []                                       # (weights in place, kind, target, stride, loss slot, lr)
         for i in range(NA):
+            lr_i = self.fast_lr[i]
             if lab[i] == MALICIOUS:
                 k = mal.index(i)
-                chains.append((self.critic_local[i], L.IN_S, self.tdt_local[k], 1, None))
-                chains.append((self.tr[i], L.IN_SA, self.neg_r_coop, 1, self.loss_t[i:i + 1]))
-                chains.append((self.critic[i], L.IN_S, self.tdt[i], 1, self.loss_c[i:i + 1]))
+                chains.append((self.critic_local[i], L.IN_S, self.tdt_local[k], 1, None, lr_i))
+                chains.append((self.tr[i], L.IN_SA, self.neg_r_coop, 1, self.loss_t[i:i + 1], lr_i))
+                chains.append((self.critic[i], L.IN_S, self.tdt[i], 1, self.loss_c[i:i + 1], lr_i))
             elif lab[i] == GREEDY:
-                chains.append((self.tr[i], L.IN_SA, r_col[i], NA, self.loss_t[i:i + 1]))
-                chains.append((self.critic[i], L.IN_S, self.tdt[i], 1, self.loss_c[i:i + 1]))
+                chains.append((self.tr[i], L.IN_SA, r_col[i], NA, self.loss_t[i:i + 1], lr_i))
+                chains.append((self.critic[i], L.IN_S, self.tdt[i], 1, self.loss_c[i:i + 1], lr_i))
 
         cons_jobs, team_jobs, team_apply = [], [], []
         for n, i in enumerate(coop):
             nodes = self.in_nodes[i]
-            cons_jobs.append(ops.consensus_job(self.critic[i], self.msg_c, self.PC, nets.n_hidden_params(2 * NA), nodes, self.H))
-            cons_jobs.append(ops.consensus_job(self.tr[i], self.msg_t, self.PT, nets.n_hidden_params(3 * NA), nodes, self.H))
-            team_jobs.append(ops.team_job(self.critic[i], L.IN_S, self.msg_c, self.PC, nodes, self.H, sums=self.sums_team[2 * n]))
-            team_jobs.append(ops.team_job(self.tr[i], L.IN_SA, self.msg_t, self.PT, nodes, self.H, sums=self.sums_team[2 * n + 1]))
+            cons_jobs.append(ops.consensus_job(self.critic[i], self.msg_c, self.PC, nets.n_hidden_params(2 * NA), nodes, self.H[i]))
+            cons_jobs.append(ops.consensus_job(self.tr[i], self.msg_t, self.PT, nets.n_hidden_params(3 * NA), nodes, self.H[i]))
+            team_jobs.append(ops.team_job(self.critic[i], L.IN_S, self.msg_c, self.PC, nodes, self.H[i], sums=self.sums_team[2 * n]))
+            team_jobs.append(ops.team_job(self.tr[i], L.IN_SA, self.msg_t, self.PT, nodes, self.H[i], sums=self.sums_team[2 * n + 1]))
             team_apply.append(ops.sgd_job(self.critic[i], self.critic[i], self.sums_team[2 * n], self.PC, -1.0 / Bg, first=self.PC - 21))
             team_apply.append(ops.sgd_job(self.tr[i], self.tr[i], self.sums_team[2 * n + 1], self.PT, -1.0 / Bg, first=self.PT - 21))
         cons_jobs, team_jobs, team_apply = arr(L.ConsensusJob, cons_jobs), arr(L.TeamJob, team_jobs), arr(L.SgdJob, team_apply)
@@ -317,7 +339,7 @@ class Trainer:
                     self.launches += 3
             if chains:
                 self._timed("minibatch_sgd", self._minibatch_sgd, chains, T)
-            for i in range(NA):                                            # the transmitted messages (:118-121)
+            for i in range(self.n_real):                                   # the transmitted messages (:118-121)
                 if lab[i] != COOP:
                     self.msg_c[i].copy_(self.critic[i])
                     self.msg_t[i].copy_(self.tr[i])
@@ -334,7 +356,7 @@ class Trainer:
         a0 = (T - Ta) * N
         rows_act = self._rows(a0, Ta * N)
         d_jobs = []
-        for i in range(NA):
+        for i in range(self.n_real):
             if lab[i] == COOP:                                             # res..py:95-98
                 d_jobs.append(ops.value_job(self.delta[i], [(self.tr[i], L.IN_SA, 1.0), (self.critic[i], L.IN_NS, self.gamma),
                                                             (self.critic[i], L.IN_S, -1.0)]))
@@ -357,13 +379,14 @@ class Trainer:
             self._allreduce(self.sums_actor[:len(coop)])
             ops.adam_apply(arr(L.AdamJob, aj))
             self.launches += 3
-        adv = [i for i in range(NA) if lab[i] != COOP]
+        adv = [i for i in range(self.n_real) if lab[i] != COOP]
         if adv:
             self._minibatch_adam(adv, T, Ta, a0)
 
-        losses = dict(critic_loss=self.loss_c.cpu().numpy().astype(np.float64),
-                      TR_loss=self.loss_t.cpu().numpy().astype(np.float64),
-                      actor_loss=self.loss_a.cpu().numpy().astype(np.float64))
+        n = self.n_real
+        losses = dict(critic_loss=self.loss_c.cpu().numpy().astype(np.float64)[:n],
+                      TR_loss=self.loss_t.cpu().numpy().astype(np.float64)[:n],
+                      actor_loss=self.loss_a.cpu().numpy().astype(np.float64)[:n])
         self.d2h_bytes += 3 * 8 * NA
         # ---------------- IV) buffer trim (:158-163)
         self.trim()
@@ -378,7 +401,8 @@ class Trainer:
         self.h2d_bytes += 4 * perms.numel()
         base = perms.data_ptr()
         gj, aj = [], []
-        for c, (w, kind, tgt, st, loss) in enumerate(chains):
+        lrs = [ch[5] if len(ch) > 5 else self.fast_lr[0] for ch in chains]
+        for c, (w, kind, tgt, st, loss) in enumerate([ch[:5] for ch in chains]):
             n = self.PT if kind == L.IN_SA else self.PC
             sums = self.sums_mb[c][:n + 1]
             gj.append(ops.grad_job(w, tgt, sums, kind, target_stride=st, time_idx=perms))
@@ -392,17 +416,24 @@ class Trainer:
         if self.world == 1 or self.comm is not None:       # whole fit in one library call (fused reduce [+ exchange] + apply)
             for c in range(nC):
                 gj[c].time_idx = base + 4 * (c * E * T)
-            ops.minibatch_sgd(rows, gj, aj, E, T, self.mb_times, self.fast_lr, self.ws)
+            if self.mb_cells is not None:                   # one persistent kernel for the whole fit
+                for c in range(nC):
+                    aj[c].coef = lrs[c]                     # per-chain learning rate
+                ops.minibatch_fit(rows, gj, aj, E, T, self.mb_times, lrs[0], self.mb_cells)
+                self.launches += 1
+                return
+            if len(set(lrs)) != 1:
+                raise L.RcmarlError("the launch-chain mini-batch path takes one learning rate; use the persistent kernel")
+            ops.minibatch_sgd(rows, gj, aj, E, T, self.mb_times, lrs[0], self.ws)
             self.launches += 2 * nb_steps
             return
         for e in range(E):
             for b in range(nb):
                 cnt = min(self.mb_times, T - b * self.mb_times)
                 rows.n_rows = cnt * N
-                coef = self.fast_lr * 2.0 / (cnt * N * self.world)
                 for c in range(nC):
                     gj[c].time_idx = base + 4 * ((c * E + e) * T + b * self.mb_times)
-                    aj[c].coef = coef
+                    aj[c].coef = lrs[c] * 2.0 / (cnt * N * self.world)
                     if e == 1 and b == 0:
                         aj[c].loss_out = None                              # history['loss'][0]: epoch 0 only
                 ops.grad(rows, gj, L.LOSS_MSE, self.ws)

@@ -149,6 +149,9 @@ class Sequential(Model):
                                       "Flatten, Dense(20, LeakyReLU(0.1)) x2, Dense(n_out[, softmax]) (main.py:60-82)")
         self.n_agents, self.n_feat = spec.shape
         self.d_in = self.n_agents * self.n_feat
+        # the kernels are instantiated for 5 and 16 agents; other team sizes run zero-padded (rcmarl/nets.py)
+        self.n_kernel = nets.kernel_agents(self.n_agents)
+        self.d_in_k = self.n_kernel * self.n_feat
         self.n_out = dense[2].units
         self.softmax = dense[2].activation == 'softmax'
         if self.n_out not in (1, N_ACTIONS) or self.n_feat not in (2, 3):
@@ -163,21 +166,22 @@ class Sequential(Model):
     # -- parameters ---------------------------------------------------------
     @property
     def n_params(self):
-        return param_count(self.d_in, self.n_out)
+        """Length of the packed DEVICE vector (the kernel instantiation's input width)."""
+        return param_count(self.d_in_k, self.n_out)
 
     @property
     def flat(self):
         """Packed parameters in device memory (allocated on first use)."""
         if self._flat is None:
             import torch
-            self._flat = torch.as_tensor(nets.pack(self._host)).to("cuda")
+            self._flat = torch.as_tensor(nets.pack_padded(self._host, self.d_in_k)).to("cuda")
             self._host = None
         return self._flat
 
     def get_weights(self):
         if self._flat is None:
             return [a.copy() for a in self._host]
-        return nets.unpack(self._flat.detach().cpu().numpy(), self.d_in, self.n_out)
+        return nets.unpack_padded(self._flat.detach().cpu().numpy(), self.d_in, self.d_in_k, self.n_out)
 
     def set_weights(self, w):
         w = [np.asarray(a, np.float32) for a in w]
@@ -188,7 +192,7 @@ class Sequential(Model):
             self._host = [a.copy() for a in w]
         else:
             import torch
-            self._flat.copy_(torch.as_tensor(nets.pack(w)))
+            self._flat.copy_(torch.as_tensor(nets.pack_padded(w, self.d_in_k)))
 
     @property
     def inputs(self):
@@ -208,10 +212,11 @@ class Sequential(Model):
         if x.shape[1] != self.d_in:
             raise ValueError(f"expected input with {self.d_in} features per row, got {x.shape[1]}")
         out = torch.empty(B, self.n_out, dtype=torch.float32, device=x.device)
+        x = nets.pad_agent_slots(x, self.n_agents, self.n_kernel)
         if self.n_feat == 3:
-            rows, kind = ops.make_rows(x, None, None, self.n_agents), L.IN_SA
+            rows, kind = ops.make_rows(x, None, None, self.n_kernel), L.IN_SA
         else:
-            rows, kind = ops.make_rows(None, x, None, self.n_agents), L.IN_NS
+            rows, kind = ops.make_rows(None, x, None, self.n_kernel), L.IN_NS
         ops.values(rows, [ops.value_job(out, [(self.flat, kind, 1.0)], n_out=self.n_out, softmax=int(self.softmax))])
         return out
 

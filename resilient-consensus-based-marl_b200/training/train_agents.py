@@ -36,8 +36,9 @@ def build_trainer(env, agents, args, exp_buffer=None, **overrides):
     labels = list(args['agent_label'])
     weights = [ag.get_parameters() for ag in agents]
     slow_lr = [float(getattr(ag, 'slow_lr', args.get('slow_lr', 0.01))) for ag in agents]
-    fast = [float(ag.fast_lr) for ag in agents if hasattr(ag, 'fast_lr')]
-    H = [int(ag.H) for ag in agents if hasattr(ag, 'H')]
+    # per-agent hyper-parameters, as the reference stores them (agents/resilient_CAC_agents.py:28-36)
+    fast = [float(getattr(ag, 'fast_lr', args.get('fast_lr', 0.01))) for ag in agents]
+    H = [int(getattr(ag, 'H', 0)) for ag in agents]
     adam = [(ag.adam.m, ag.adam.v, ag.adam.t) if getattr(ag, 'adam', None) is not None and ag.adam.m is not None else None
             for ag in agents]
     rank, world = _dist_info()
@@ -45,8 +46,7 @@ def build_trainer(env, agents, args, exp_buffer=None, **overrides):
     scaling = bool(np.any(np.asarray(getattr(env, 'std_state', 1)) != 1) or np.any(np.asarray(getattr(env, 'mean_state', 0)) != 0))
     fixed0 = None if getattr(env, 'randomize_state', True) else env.initial_state
     kw = dict(scaling=scaling, fixed_initial_state=fixed0, labels=labels, in_nodes=args['in_nodes'], weights=weights, desired=env.desired_state,
-              n_envs=getattr(env, 'n_envs', 1), nrow=env.nrow, ncol=env.ncol, gamma=args['gamma'], H=H[0] if H else 0,
-              fast_lr=fast[0] if fast else args.get('fast_lr', 0.01), slow_lr=slow_lr, max_ep_len=args['max_ep_len'],
+              n_envs=getattr(env, 'n_envs', 1), nrow=env.nrow, ncol=env.ncol, gamma=args['gamma'], H=H, fast_lr=fast, slow_lr=slow_lr, max_ep_len=args['max_ep_len'],
               n_ep_fixed=args['n_ep_fixed'], n_epochs=args['n_epochs'], buffer_size=args['buffer_size'],
               common_reward=bool(args['common_reward']), seed=int(args.get('random_seed', 0)), adam_state=adam,
               rank=rank, world=world)

@@ -449,3 +449,60 @@ def test_env_step_matches_reference_fixture(K):
             rew = K.ops.env_step(state, act, des, nrow)
             assert np.array_equal(state.cpu().numpy()[0], S[t + 1])
             assert np.array_equal(rew.cpu().numpy()[0], z[f"{tag}/reward_scaled"][t].astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("NA,nrow,N,T", [(5, 5, 64, 40), (5, 5, 24, 37), (16, 10, 64, 33), (5, 5, 1, 96)])
+def test_minibatch_fit_persistent_kernel_matches_oracle_and_launch_chain(K, NA, nrow, N, T):
+    """rcmarl_minibatch_fit (ONE persistent kernel: parameters resident in shared memory, cross-CTA reduction through
+    {value, sequence} cells) against (a) the fp64 oracle's fit_minibatch with the same injected permutations
+    (agents/adversarial_CAC_agents.py:133,150,163: fit(batch_size=32, epochs=E), Appendix C batching) and (b) the
+    round-1 launch chain rcmarl_minibatch_sgd; and bitwise reproducibility of two runs."""
+    rs = np.random.RandomState(NA + N + T)
+    E, mb, lr = 3, 32, 0.01
+    B = N * T
+    s, ns, a, r = synth(rs, B, NA, nrow)
+    sa = np.concatenate([s, a], -1)
+    kinds = [K.L.IN_S, K.L.IN_SA, K.L.IN_S]
+    nets0 = [rand_net(rs, 3 * NA if k == K.L.IN_SA else 2 * NA, 1) for k in kinds]
+    tgts = [rs.randn(B).astype(np.float32) for _ in kinds]
+    perms = np.stack([np.stack([rs.permutation(T) for _ in range(E)]) for _ in kinds]).astype(np.int32)     # [C, E, T]
+    dsa, dns, dr = to_dev(K, sa.reshape(B, -1), ns.reshape(B, -1), r.reshape(B, -1))
+    dperm = to_dev(K, perms)[0]
+    dt = to_dev(K, *tgts)
+
+    def run(persistent):
+        ws = [to_dev(K, K.nets.pack(w))[0] for w in nets0]
+        loss = torch.zeros(len(kinds), device=K.dev)
+        gj, aj = [], []
+        for c, kind in enumerate(kinds):
+            n = ws[c].numel()
+            sums = torch.zeros(n + 1, device=K.dev)
+            g = K.ops.grad_job(ws[c], dt[c], sums, kind, time_idx=dperm)
+            g.time_idx = dperm.data_ptr() + 4 * c * E * T
+            gj.append(g)
+            aj.append(K.ops.sgd_job(ws[c], ws[c], sums, n, 0.0, loss_out=loss[c:c + 1], loss_coef=1.0 / B, loss_accumulate=1))
+        rows = K.ops.make_rows(dsa, dns, dr, NA, 0, 0, dperm, N)
+        if persistent:
+            cells = K.ops.MinibatchCells(len(kinds), K.L.param_count(3 * NA, 1))
+            K.ops.minibatch_fit(rows, gj, aj, E, T, mb, lr, cells)
+            K.ops.minibatch_fit(rows, gj, aj, E, T, mb, 0.0 * lr + 1e-30, cells)     # second call on the same cells: a no-op step size
+        else:
+            K.ops.minibatch_sgd(rows, gj, aj, E, T, mb, lr)
+        torch.cuda.synchronize()
+        return [w.cpu().numpy() for w in ws], loss.cpu().numpy()
+    w_p, loss_p = run(True)
+    w_p2, _ = run(True)
+    w_c, loss_c = run(False)
+    for c, kind in enumerate(kinds):
+        assert np.array_equal(w_p[c], w_p2[c])                                 # fixed-order reductions
+        x = O.flatten_rows(sa if kind == K.L.IN_SA else s, np.float64)
+        rp = [O.expand_time_perm(perms[c, e], N) for e in range(E)]
+        w64, l64 = O.fit_minibatch(O.cast_weights(nets0[c], np.float64), x, tgts[c].astype(np.float64).reshape(-1, 1), lr, E,
+                                   mb * N, rp)
+        want = K.nets.pack(w64)
+        np.testing.assert_allclose(w_p[c], want, rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(w_p[c], w_c[c], rtol=1e-5, atol=1e-6)
+        # the second (tiny step size) call accumulated its own epoch-0 loss on top: compare the first call's share only
+        np.testing.assert_allclose(loss_c[c], l64, rtol=1e-4)
+    assert np.all(loss_p > loss_c * 1.05)                                      # two calls accumulated two epoch-0 losses

@@ -199,3 +199,67 @@ def test_env_options_scaling_off_and_fixed_initial_state():
     ns_y = tall.ns[:20 * 6 * 64].cpu().numpy().reshape(-1, 5, 2)[:, :, 1]
     assert set(np.unique(ns_y)) <= set(ty.tolist())          # no zero table entries: every reachable y is scaled
     assert ns_y.max() > ty[3] + 1e-6                          # ... and y does leave [0, ncol)
+
+
+@pytest.mark.parametrize("NA,nrow,Hs", [(3, 3, [1, 1, 1]), (4, 5, [0, 1, 1, 0]), (7, 6, [2, 1, 2, 0, 1, 2, 1])])
+def test_other_team_sizes_and_per_agent_H_match_oracle(NA, nrow, Hs):
+    """main.py:26 takes any --n_agents (the reference's env_test.py uses 3 agents on a 3x3 grid) and the reference stores H
+    and fast_lr per agent (agents/resilient_CAC_agents.py:28-36).  Teams of 3 / 4 / 7 agents run on the 5- / 16-agent kernel
+    instantiations with zero agent slots; every agent has its own H and fast learning rate; one agent is greedy."""
+    need_gpu()
+    from rcmarl.trainer import Trainer
+    from rcmarl import nets
+    rs = np.random.RandomState(NA)
+    N, T1, gamma = 6, 40, 0.9
+    labels = ['Cooperative'] * NA
+    labels[-1] = 'Greedy'
+    n_in = min(NA, 4)
+    in_nodes = [[(i + k) % NA for k in range(n_in)] for i in range(NA)]
+    fast = [0.01 + 0.002 * i for i in range(NA)]
+    w = [[nets.glorot_uniform(2 * NA, 5, rs), nets.glorot_uniform(2 * NA, 1, rs), nets.glorot_uniform(3 * NA, 1, rs)] for _ in range(NA)]
+    desired = rs.randint(0, nrow, size=(NA, 2))
+    agents = []
+    for i in range(NA):
+        if labels[i] == 'Greedy':
+            agents.append(O.GreedyOracleAgent(w[i][0], w[i][1], w[i][2], 0.002, fast[i], gamma, dtype=np.float64))
+        else:
+            agents.append(O.RPBCACOracleAgent(w[i][0], w[i][1], w[i][2], 0.002, fast[i], gamma, H=Hs[i], dtype=np.float64))
+    used = []
+    prs = np.random.RandomState(5)
+
+    def rec(T):
+        p = prs.permutation(T)
+        used.append(p)
+        return p
+    B = T1 * N
+    pos = rs.randint(0, nrow, size=(B, NA, 2))
+    npos = np.clip(pos + rs.randint(-1, 2, size=pos.shape), 0, nrow - 1)
+    mean, std = (nrow - 1) / 2.0, np.std(np.arange(nrow))
+    s = ((pos - mean) / std).astype(np.float32)
+    ns = ((npos - mean) / std).astype(np.float32)
+    a = rs.randint(0, 5, size=(B, NA, 1)).astype(np.float32)
+    r = (-rs.randint(0, 2 * nrow, size=(B, NA, 1)) / 5.0).astype(np.float32)
+    want = O.update_round(agents, labels, in_nodes, s, ns, a, r, n_envs=N, n_epochs=2, n_actor_steps=T1,
+                          common_reward=False, perm_source=rec)
+    it = iter(list(used))
+    tr = Trainer(labels=labels, in_nodes=in_nodes, weights=w, desired=desired, n_envs=N, nrow=nrow, ncol=nrow, gamma=gamma,
+                 H=Hs, fast_lr=fast, slow_lr=0.002, max_ep_len=8, n_ep_fixed=5, n_epochs=2, buffer_size=100,
+                 perm_source=lambda T: next(it))
+    tr.load_rows(s, ns, a, r)
+    got = tr.update_round()
+    assert next(it, None) is None
+    for k in ("critic_loss", "TR_loss", "actor_loss"):
+        np.testing.assert_allclose(got[k][:NA], want[k], rtol=2e-3, atol=2e-5, err_msg=k)
+    for i in range(NA):
+        gw = tr.get_weights(i)
+        assert gw[0][0].shape == (2 * NA, 20) and gw[2][0].shape == (3 * NA, 20)
+        close_w(gw, agents[i].get_parameters())
+    # the unused agent slots stayed exactly zero (inputs, W1 rows, Adam slots)
+    NK = tr.NA
+    assert float(tr.tr[:NA].view(NA, -1)[:, 3 * NA * 20:3 * NK * 20].abs().max()) == 0.0
+    assert float(tr.actor[:NA].view(NA, -1)[:, 2 * NA * 20:2 * NK * 20].abs().max()) == 0.0
+    # and a rollout block only moves the real agents
+    e, rt = tr.rollout_block()
+    assert e.shape == (5, NA) and rt.shape == (5, NA)
+    rows = tr.sa[tr.t_filled * N - 8 * 5 * N:tr.t_filled * N].view(-1, NK, 3)
+    assert float(rows[:, NA:].abs().max()) == 0.0 and float(rows[:, :NA, :2].abs().max()) > 0.0

@@ -106,7 +106,9 @@ def cmp(a, b):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "dump":
+    if sys.argv[1] == "time":
+        timing()
+    elif sys.argv[1] == "dump":
         dump(sys.argv[2])
         timing()
     else:

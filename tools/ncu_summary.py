@@ -47,7 +47,7 @@ if hi:
         key = ".".join(op.split(".")[:2]) if op.startswith(("LDS", "STS", "LDG", "STG")) else op.split(".")[0]
         n = int(r[ix["Instructions Executed"]])
         by[key] += n; tot += n
-        wf[key] += int(r[ix["L1 Wavefronts Shared"]])
+        wf[key] += int(r[ix["L1 Wavefronts Shared"]]) if "L1 Wavefronts Shared" in ix else 0   # column absent when a kernel uses no shared memory
         smp[key] += int(r[ix["# Samples"]])
         for k in ix:
             if k.startswith("stall_") and "Not Issued" not in k:

@@ -1,0 +1,37 @@
+"""Stand-alone driver for the mini-batch chain at the C2 shape (one rcmarl_minibatch_fit call = 940 SGD steps over
+131 072-row mini-batches for the malicious agent's three chains), for ncu captures and A/B timing:
+   python tools/prof_mb.py [n_envs=4096] [T=3000] [reps=3]          (RCMARL_MB_PERSIST=0: round-1 launch chain)
+Prints CUDA-event timings per call and per step when run without a profiler."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "resilient-consensus-based-marl_b200"))
+import bench                                           # noqa: E402
+from rcmarl.trainer import Trainer                     # noqa: E402
+from rcmarl import _lib as L                            # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+cfg = bench.workload("C2", N)
+tr = Trainer(seed=1, **cfg)
+while tr.t_filled < T:
+    tr.rollout_block(min(cfg["n_ep_fixed"], (T - tr.t_filled) // cfg["max_ep_len"]))
+i = cfg["labels"].index("Malicious")
+tr.tdt_local[0].normal_(); tr.tdt[i].normal_(); tr.neg_r_coop.normal_()
+chains = [(tr.critic_local[i], L.IN_S, tr.tdt_local[0], 1, None), (tr.tr[i], L.IN_SA, tr.neg_r_coop, 1, tr.loss_t[i:i + 1]),
+          (tr.critic[i], L.IN_S, tr.tdt[i], 1, tr.loss_c[i:i + 1])]
+ts = []
+for _ in range(reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); tr._minibatch_sgd(chains, tr.t_filled); b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+steps = tr.mb_epochs * ((tr.t_filled + tr.mb_times - 1) // tr.mb_times)
+print(f"minibatch chain: n_envs={N} T={tr.t_filled} steps={steps} persistent={tr.mb_cells is not None} "
+      f"ms_per_call={np.median(ts):.3f} us_per_step={1e3 * np.median(ts) / steps:.2f} (all: {[round(t, 2) for t in ts]})")
