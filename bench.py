@@ -361,7 +361,7 @@ def main():
             t_tot += float(np.sum(prof["minibatch_sgd"]))
             f_tot += flops_call * len(prof["minibatch_sgd"])
         tf_w = f_tot / (t_tot * 1e-3) / 1e12
-        roof = dict(kernel="grad_kernel<5,MSE> (fused MLP forward/backward; rcmarl_grad + rcmarl_minibatch_sgd)",
+        roof = dict(kernel=f"grad_kernel<{tr.NA},MSE> (fused MLP forward/backward; rcmarl_grad + rcmarl_minibatch_fit)",
                     bound="fp32", achieved=tf_w, peak=fp32_peak, unit="TFLOP/s", frac=tf_w / fp32_peak,
                     frac_is="time-weighted over both regimes of the kernel (full-batch fits + mini-batch chains)",
                     share_of_step=t_tot / ms, traffic=grad_traffic(args.workload),
@@ -384,7 +384,7 @@ def main():
         out = torch.empty(1 << 20, device="cuda")
         cons = {}
         reps = 12
-        for H in (0, 1, 4):
+        for H in (0, 1, 2, 4):
             for i in range(3):
                 ops.clip_mean(Xs[i], H, out)
             ts = []

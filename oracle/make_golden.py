@@ -18,6 +18,7 @@ container (needs /root/reference, which does not exist on the GPU box).
                            verbatim on seeded inputs with injected fit permutations,
                            plus train_RPBCAC verbatim for 3 cooperative + 1 greedy +
                            1 faulty agent with common_reward=True (2 update rounds).
+7. ref_main_py.npz         the reference driver main.py as a compressed blob (executed unchanged by tests/test_main_gpu.py).
 6. ref_learning.npz        start weights / task / last-500-episode means of sim_data2.pkl
                            for the 45 published run directories (tools/learning_harness.py).
 """
@@ -423,6 +424,18 @@ def make_learning_fixture():
     print("learning fixture:", len(runs), "runs,", len(out), "arrays")
 
 
+def make_main_fixture():
+    """The reference driver main.py, byte for byte, as a zlib blob inside a fixture (NOT a source file of this repo): the
+    GPU box has no reference checkout, and tests/test_main_gpu.py must execute the UNCHANGED driver through real training
+    (main.py:117-121).  The SHA-256 of the original is stored next to it."""
+    import hashlib
+    import zlib
+    raw = open(os.path.join(REF, "main.py"), "rb").read()
+    np.savez(os.path.join(OUT, "ref_main_py.npz"), blob=np.frombuffer(zlib.compress(raw, 9), np.uint8),
+             sha256=np.array(hashlib.sha256(raw).hexdigest()), n_bytes=np.int64(len(raw)))
+    print("main.py fixture:", len(raw), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_kat()
@@ -431,3 +444,4 @@ if __name__ == "__main__":
     make_train_run()
     make_adversaries()
     make_learning_fixture()
+    make_main_fixture()

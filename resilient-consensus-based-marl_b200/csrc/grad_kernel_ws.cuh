@@ -1,0 +1,491 @@
+// grad_kernel_ws.cuh -- warp-specialised fused forward + backward of the scalar-output nets (critic / team reward) at
+// n_agents = 5: tensor cores (tcgen05, 3xTF32) for the three dense products of a row, CUDA cores for the weight-gradient
+// outer products, in different warps of one CTA (replaces the fwd/bwd inside critic.fit / TR.fit,
+// agents/resilient_CAC_agents.py:118,136 and agents/adversarial_CAC_agents.py:133,150,163).
+//
+// Why: grad_kernel (grad_kernel.cuh) runs both phases in every warp.  Its phase 1 feeds the FMA pipes from shared memory
+// (2 wavefronts per weight quad) and keeps 64 phase-2 accumulators alive meanwhile, so neither the FMA pipes (60 %) nor
+// the shared-memory pipe (74 %) saturate (profiles/r01_final_ncu.md).  The first tensor-core version (grad_kernel_tc.cuh)
+// moved the dense products to tcgen05 but kept both phases in one thread: each 128-row tile then waits for three MMA round
+// trips in sequence and ran SLOWER (12.1 vs 10.0 ms).  Here the two halves are decoupled:
+//
+//   producer groups (2 x 4 warps, thread = buffer row = TMEM lane, ~100 registers)
+//       z1 = [x | 1] . [W1; b1]   ->  h1 = lrelu(z1)          tcgen05.mma, A operand written to TMEM by the row's thread as
+//       z2 = [h1 | 1] . [W2; b2]  ->  h2, out, e, delta2       tf32 hi / lo halves, B = split weights in shared memory,
+//       u  = delta2 . W2^T        ->  delta1 = u * lrelu'(h1)  accumulator read back with tcgen05.ld
+//     and write the row's [x | h1 | delta1 | delta2] into a shared-memory tile buffer (ring of WS_NBUF 128-row buffers);
+//     the output-layer gradient (21 values) and the loss are accumulated per thread.
+//   consumer warps (4, one per scheduler, 240 registers)
+//       sum over the buffer's rows of the outer products [x | 1] (x) delta1 and [h1 | 1] (x) delta2 as 8 x 20 register
+//       tiles (5 tiles x 6 row groups per warp; 7 LDS.128 per 80 FFMA2), accumulated across ALL tiles of the CTA.
+//   Buffers are handed over with full / empty mbarriers; tile q goes to producer group q % 2, buffer q % WS_NBUF and
+//   consumer q % 4 (static, so every sum keeps a fixed order: results are bitwise reproducible).
+// While a producer group waits for its MMAs the other group and the consumers own the issue slots; the MMAs themselves
+// run beside the FMA pipes.
+#pragma once
+#include "grad_kernel_tc.cuh"
+
+namespace rcmarl {
+
+#ifndef RCMARL_WS_GROUPS
+#define RCMARL_WS_GROUPS 2
+#endif
+constexpr int WS_GROUPS = RCMARL_WS_GROUPS;                   // producer groups of 4 warps (2 or 3)
+constexpr int WS_CONS = 4;                                    // consumer warps
+constexpr int WS_WARPS = 4 * WS_GROUPS + WS_CONS;             // 12
+constexpr int WS_THREADS = 32 * WS_WARPS;                     // 384
+constexpr int WS_NBUF = 5;                                    // tile buffers in the ring
+constexpr int WS_ROWF = 76;                                   // floats per buffer row: x 16 | h1 20 | delta1 20 | delta2 20
+constexpr int WS_OX = 0, WS_OH1 = 16, WS_OD1 = 36, WS_OD2 = 56;
+constexpr int WS_TILE_ROWS = 128;
+constexpr int WS_NG = 6;                                      // row groups per consumer warp (5 tiles x 6 groups = 30 lanes)
+// setmaxnreg targets (multiples of 8): 2 groups: 256 x 128 + 128 x 240 = 63 488 registers; 3 groups: 384 x 96 + 128 x 216 = 64 512
+constexpr int WS_REGS_PROD = WS_GROUPS == 2 ? 128 : 96, WS_REGS_CONS = WS_GROUPS == 2 ? 240 : 216;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// mbarrier wait with back-off.  try_wait returns after a few tens of nanoseconds whether or not the phase completed, so a
+// plain poll loop is ~6 instructions per iteration per waiting warp; in the first version a third of all issued instructions
+// were wait loops, and they competed for issue slots with the consumer warp of the same scheduler (the FMA pipes were 45 %
+// busy while the producers waited for free buffers).  Sleeping between polls hands those slots to the warps that compute.
+// A barrier that never completes ends in a trap (~1 s), not a hang.
+template <int FIRST_NS, int NS>
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, polls = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (FIRST_NS > 0) __nanosleep(FIRST_NS);
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(NS);
+        if (++polls > (1u << 23)) __trap();
+    }
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// tf32 hi / lo halves of this thread's K operand values -> TMEM columns [col_hi, col_hi + K) and [col_lo, col_lo + K) of its
+// lane, 8 columns at a time (16 live temporaries instead of 2 K: the producers run on a 128-register budget)
+template <int K>
+__device__ __forceinline__ void ws_store_operand(uint32_t tlane, int col_hi, int col_lo, const float (&v)[K]) {
+    static_assert(K % 8 == 0, "operand width");
+#pragma unroll
+    for (int c = 0; c < K / 8; ++c) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float hv = to_tf32(v[8 * c + k]);
+            h[k] = __float_as_uint(hv);
+            l[k] = __float_as_uint(v[8 * c + k] - hv);
+        }
+        tmem_st8(tlane + col_hi + 8 * c, h);
+        tmem_st8(tlane + col_lo + 8 * c, l);
+    }
+}
+
+constexpr int ws_smem_floats() {
+    // packed net | alignment slack | B operands (hi + lo of 32x16, 32x24, 32x24) | tile buffers | barriers + tmem slot
+    return round32(param_count(15, 1)) + 32 + 2 * TC_N * 16 + 4 * TC_N * 24 + WS_NBUF * WS_TILE_ROWS * WS_ROWF + 64;
+}
+
+// packed-parameter index of element (ii, j) of consumer tile t (a rows 8 t .. 8 t + 7 of [x | 1] for t < 2, of [h1 | 1] else)
+template <int DIN>
+__device__ __forceinline__ int ws_tile_param(int t, int ii, int j) {
+    if (t < 2) {
+        const int i = 8 * t + ii;
+        return i < DIN ? i * HID + j : (i == DIN ? off_b1(DIN) + j : -1);
+    }
+    const int i = 8 * (t - 2) + ii;
+    return i < HID ? off_W2(DIN) + i * HID + j : (i == HID ? off_b2(DIN) + j : -1);
+}
+
+// consumer: acc[8][20] += a (x) delta for one buffer row (7 LDS.128, 80 FFMA2 with a broadcast scalar operand)
+__device__ __forceinline__ void ws_consume_row(const float* __restrict__ rp, int acol, int dcol, bool last_tile, f2 (&acc)[80]) {
+    const float4 a0 = *reinterpret_cast<const float4*>(rp + acol);
+    float4 a1 = *reinterpret_cast<const float4*>(rp + acol + 4);
+    if (last_tile) a1 = make_float4(1.f, 0.f, 0.f, 0.f);
+    f2 d[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(rp + dcol + 4 * k);
+        d[2 * k] = pack2(v.x, v.y);
+        d[2 * k + 1] = pack2(v.z, v.w);
+    }
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+        const f2 aa = pack2(a[ii], a[ii]);
+#pragma unroll
+        for (int jp = 0; jp < 10; ++jp) acc[ii * 10 + jp] = fma2(aa, d[jp], acc[ii * 10 + jp]);
+    }
+}
+
+// inputs of row r of tile q of this CTA: features, target, and whether the row exists
+template <int NA, int DIN>
+__device__ __forceinline__ void ws_fetch(const rcmarl_rows& Rw, const rcmarl_grad_job& job, int y, int gy, int q, int r,
+                                         float (&xr)[DIN], float& tgt, bool& live) {
+    const int64_t m = ((int64_t)y + (int64_t)q * gy) * WS_TILE_ROWS + r;
+    live = m < Rw.n_rows;
+    const int64_t row = row_of(Rw, live ? m : 0);
+    load_x<NA, DIN>(Rw, job.kind, row, xr);
+    tgt = live ? __ldg(job.target + row * job.target_stride) : 0.f;
+}
+
+// ---- shared-memory layout (the same for both nets: the parameter region is sized for the larger one) ----
+struct WsShared {
+    float *sw, *b1h, *b1l, *b2h, *b2l, *b3h, *b3l, *bufs;
+    uint64_t *full, *empty, *mma_bar;
+    uint32_t* tslot;
+};
+__device__ __forceinline__ WsShared ws_carve(float* smem) {
+    constexpr int NPMAX = param_count(15, 1);
+    WsShared S;
+    S.sw = smem;
+    // 128-byte alignment by OFFSET arithmetic on the shared-memory pointer: a round trip through uintptr_t would make every
+    // later access a generic LD / ST (L1TEX path, long scoreboard) instead of LDS / STS -- measured in the first version
+    const uint32_t sbase = smem_u32(smem + NPMAX);
+    S.b1h = smem + NPMAX + (((sbase + 127u) & ~127u) - sbase) / 4u;
+    S.b1l = S.b1h + TC_N * 16;
+    S.b2h = S.b1l + TC_N * 16;
+    S.b2l = S.b2h + TC_N * 24;
+    S.b3h = S.b2l + TC_N * 24;
+    S.b3l = S.b3h + TC_N * 24;
+    S.bufs = S.b3l + TC_N * 24;                                       // [WS_NBUF][128][WS_ROWF]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(S.bufs + WS_NBUF * WS_TILE_ROWS * WS_ROWF);
+    S.full = bars;                                                    // [WS_NBUF]  producers -> consumer (4 warp arrivals)
+    S.empty = bars + WS_NBUF;                                         // [WS_NBUF]  consumers -> producers (WS_CONS arrivals)
+    S.mma_bar = bars + 2 * WS_NBUF;                                   // [WS_GROUPS]
+    S.tslot = reinterpret_cast<uint32_t*>(bars + 2 * WS_NBUF + WS_GROUPS);
+    return S;
+}
+// barriers + tensor memory; touches no global memory (may run before pdl_wait)
+__device__ __forceinline__ void ws_init(const WsShared& S) {
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < WS_NBUF; ++b) { mbar_init(S.full + b, 4); mbar_init(S.empty + b, WS_CONS); }
+        for (int g = 0; g < WS_GROUPS; ++g) mbar_init(S.mma_bar + g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 0) tmem_alloc_all(S.tslot);
+}
+// B operands from the staged parameters (canonical K-major, tf32 hi / lo): B1[n][k] = [W1; b1][k][n],
+// B2[n][k] = [W2; b2][k][n], B3[n][k] = W2[n][k].  All threads; followed by ws_operands_visible() + a CTA-wide barrier.
+template <int DIN>
+__device__ __forceinline__ void ws_build_operands(const WsShared& S) {
+    const float* sw = S.sw;
+    for (int i = threadIdx.x; i < TC_N * 16; i += blockDim.x) {
+        const int n = i / 16, k = i % 16;
+        const float v = n < HID ? (k < DIN ? sw[k * HID + n] : (k == DIN ? sw[off_b1(DIN) + n] : 0.f)) : 0.f;
+        const float h = to_tf32(v);
+        S.b1h[tc_canon(n, k)] = h;
+        S.b1l[tc_canon(n, k)] = v - h;
+    }
+    for (int i = threadIdx.x; i < TC_N * 24; i += blockDim.x) {
+        const int n = i / 24, k = i % 24;
+        const float v2 = n < HID ? (k < HID ? sw[off_W2(DIN) + k * HID + n] : (k == HID ? sw[off_b2(DIN) + n] : 0.f)) : 0.f;
+        const float v3 = (n < HID && k < HID) ? sw[off_W2(DIN) + n * HID + k] : 0.f;
+        const float h2v = to_tf32(v2), h3v = to_tf32(v3);
+        S.b2h[tc_canon(n, k)] = h2v;
+        S.b2l[tc_canon(n, k)] = v2 - h2v;
+        S.b3h[tc_canon(n, k)] = h3v;
+        S.b3l[tc_canon(n, k)] = v3 - h3v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic smem writes -> async-proxy (MMA) reads
+    tmem_fence_before_sync();
+}
+
+// tiles of CTA y of gy for a row set: T = y + q * gy, q = 0 .. nq - 1
+__device__ __forceinline__ int ws_tile_count(int64_t n_rows, int y, int gy) {
+    const int64_t ntiles = (n_rows + WS_TILE_ROWS - 1) / WS_TILE_ROWS;
+    return (int)((ntiles > y) ? (ntiles - y + gy - 1) / gy : 0);
+}
+
+// ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  qbase = tiles pushed through the ring by earlier
+// sweeps of the same kernel (buffer index and barrier parities continue across sweeps). ----
+template <int NA, int DIN>
+__device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows& Rw, const rcmarl_grad_job& job, int y, int gy,
+                                           int nq, uint32_t qbase, uint32_t& mph, float (&g3)[HID + 1], float& loss) {
+    constexpr int K1 = 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp >> 2, gwarp = warp & 3;
+    const int r = gwarp * 32 + lane;                                 // row of the tile = TMEM lane
+    const uint32_t tmem = *S.tslot + (uint32_t)(group * 128);        // this group's column window
+    const uint32_t tlane = tmem + ((uint32_t)(gwarp * 32) << 16);
+    constexpr int CAH = 0, CAL = 24, CD = 48;                        // A hi / lo (up to 24 columns each), accumulator (32)
+    const uint32_t idesc = umma_idesc_tf32(128, TC_N);
+    const bool issuer = (gwarp == 0) && (lane == 0);
+    uint64_t* mbar = S.mma_bar + group;
+    const SmemW W{S.sw};
+
+    // inputs of a tile: the row's features and target; loaded one tile ahead (the registers of x are free once the
+    // layer-1 operand is in TMEM, so the next tile's loads fly during the three MMA round trips of this one)
+    float xr[DIN];
+    float tgt = 0.f;
+    bool live = false;
+    if (group < nq) ws_fetch<NA, DIN>(Rw, job, y, gy, group, r, xr, tgt, live);
+
+    for (int q = group; q < nq; q += WS_GROUPS) {
+        const uint32_t Q = qbase + (uint32_t)q;
+        const int b = (int)(Q % WS_NBUF);
+        const uint32_t use = Q / WS_NBUF;
+        float* rowp = S.bufs + ((int64_t)b * WS_TILE_ROWS + r) * WS_ROWF;
+        const bool live_q = live;
+        const float tgt_q = tgt;
+        float h1[HID];
+        // ---------------- layer 1 ----------------
+        {
+            float x[K1];
+#pragma unroll
+            for (int k = 0; k < DIN; ++k) x[k] = xr[k];
+#pragma unroll
+            for (int k = DIN; k < K1; ++k) x[k] = (k == DIN) ? 1.f : 0.f;
+            mbar_wait_sleep<0, 200>(S.empty + b, (use & 1u) ^ 1u);   // the consumer is done with the buffer's previous use
+#pragma unroll
+            for (int qq = 0; qq < K1 / 4; ++qq) st4(rowp + WS_OX + 4 * qq, x[4 * qq], x[4 * qq + 1], x[4 * qq + 2], x[4 * qq + 3]);
+            ws_store_operand<K1>(tlane, CAH, CAL, x);
+            tmem_wait_st();
+            tmem_fence_before_sync();
+            named_barrier(1 + group, 128);
+            if (issuer) {
+                tmem_fence_after_sync();
+                tc_issue<K1>(tmem + CD, tmem + CAH, tmem + CAL, S.b1h, S.b1l, idesc, mbar);
+            }
+            if (q + WS_GROUPS < nq) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);   // next tile's inputs
+            mbar_wait_sleep<120, 40>(mbar, mph);
+            mph ^= 1u;
+            tmem_fence_after_sync();
+            uint32_t z[24];
+            tmem_load<24>(tlane + CD, z);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < HID; ++j) {
+                const float zz = __uint_as_float(z[j]);
+                h1[j] = fmaxf(zz, SLOPE * zz);
+            }
+        }
+        // ---------------- layer 2, output layer, delta2 ----------------
+        float d2[24];
+        {
+            float a2[24];
+#pragma unroll
+            for (int j = 0; j < HID; ++j) a2[j] = h1[j];
+            a2[20] = 1.f; a2[21] = 0.f; a2[22] = 0.f; a2[23] = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
+            ws_store_operand<24>(tlane, CAH, CAL, a2);
+            tmem_wait_st();
+            tmem_fence_before_sync();
+            named_barrier(1 + group, 128);
+            if (issuer) {
+                tmem_fence_after_sync();
+                tc_issue<24>(tmem + CD, tmem + CAH, tmem + CAL, S.b2h, S.b2l, idesc, mbar);
+            }
+            mbar_wait_sleep<120, 40>(mbar, mph);
+            mph ^= 1u;
+            tmem_fence_after_sync();
+            uint32_t z[24];
+            tmem_load<24>(tlane + CD, z);
+            tmem_wait_ld();
+            float h2[HID];
+#pragma unroll
+            for (int j = 0; j < HID; ++j) {
+                const float zz = __uint_as_float(z[j]);
+                h2[j] = fmaxf(zz, SLOPE * zz);
+            }
+            // Keras MSE (Appendix A.2): dLoss/dout = 2 (out - y) / B; the 2/B is applied by the caller
+            const float e = live_q ? head1_w<DIN>(W, h2) - tgt_q : 0.f;
+            loss = fmaf(e, e, loss);
+#pragma unroll
+            for (int j = 0; j < HID; ++j) {
+                g3[j] = fmaf(h2[j], e, g3[j]);
+                d2[j] = W.s(off_W3(DIN) + j) * e * lrelu_grad_from_out(h2[j]);
+            }
+            g3[HID] += e;
+            d2[20] = 0.f; d2[21] = 0.f; d2[22] = 0.f; d2[23] = 0.f;
+        }
+        // ---------------- backward-data: u = delta2 . W2^T, delta1 = u * lrelu'(h1) ----------------
+        {
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OD2 + 4 * qq, d2[4 * qq], d2[4 * qq + 1], d2[4 * qq + 2], d2[4 * qq + 3]);
+            ws_store_operand<24>(tlane, CAH, CAL, d2);
+            tmem_wait_st();
+            tmem_fence_before_sync();
+            named_barrier(1 + group, 128);
+            if (issuer) {
+                tmem_fence_after_sync();
+                tc_issue<24>(tmem + CD, tmem + CAH, tmem + CAL, S.b3h, S.b3l, idesc, mbar);
+            }
+            mbar_wait_sleep<120, 40>(mbar, mph);
+            mph ^= 1u;
+            tmem_fence_after_sync();
+            uint32_t u[24];
+            tmem_load<24>(tlane + CD, u);
+            tmem_wait_ld();
+            float d1[HID];
+#pragma unroll
+            for (int i = 0; i < HID; ++i) d1[i] = __uint_as_float(u[i]) * lrelu_grad_from_out(h1[i]);
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OD1 + 4 * qq, d1[4 * qq], d1[4 * qq + 1], d1[4 * qq + 2], d1[4 * qq + 3]);
+            tmem_fence_before_sync();       // the next tile's MMAs overwrite the accumulator only after the next group barrier
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(S.full + b);                       // release: this warp's 32 rows of the buffer are complete
+    }
+}
+
+// ---- consumer warp cw: tiles q = cw, cw + WS_CONS, ... of this sweep ----
+__device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, uint32_t qbase, f2 (&acc)[80]) {
+    const int lane = threadIdx.x & 31;
+    const bool active = lane < 5 * WS_NG;
+    const int atile = active ? lane % 5 : 0;
+    const int grp = active ? lane / 5 : 0;
+    const int acol = 8 * atile;                                       // x: 0..15, h1: 16..35 (tile 4: 4 values + [1 0 0 0])
+    const int dcol = atile < 2 ? WS_OD1 : WS_OD2;
+    const bool last_tile = atile == 4;
+    // Every consumer warp works on EVERY tile (steps cw, cw + WS_CONS, ... of its 22 six-row steps): a buffer is then held for
+    // a quarter of the time one warp would need for all of it, and with 5 buffers in the ring that residency -- production
+    // (three MMA round trips) plus consumption -- is what bounds the tile rate (first version: one warp per tile, producers
+    // spent most of their time waiting for a free buffer).
+    constexpr int FULL_STEPS = WS_TILE_ROWS / WS_NG;                  // 21 (+ rows 126, 127 as step 21)
+    for (int q = 0; q < nq; ++q) {
+        const uint32_t Q = qbase + (uint32_t)q;
+        const int b = (int)(Q % WS_NBUF);
+        const uint32_t use = Q / WS_NBUF;
+        mbar_wait_sleep<0, 100>(S.full + b, use & 1u);
+        const float* buf = S.bufs + (int64_t)b * WS_TILE_ROWS * WS_ROWF;
+#pragma unroll 2
+        for (int s = cw; s < FULL_STEPS; s += WS_CONS)
+            ws_consume_row(buf + (s * WS_NG + grp) * WS_ROWF, acol, dcol, last_tile, acc);
+        if (cw == FULL_STEPS % WS_CONS && grp < WS_TILE_ROWS % WS_NG)
+            ws_consume_row(buf + (FULL_STEPS * WS_NG + grp) * WS_ROWF, acol, dcol, last_tile, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(S.empty + b);
+    }
+}
+
+// ---- end of a sweep: every thread passes (A), the roles park their sums in the (now idle) tile buffers, (B), and the CTA
+// adds them up in a fixed order; store(i, v) receives the sums for the packed parameters i = 0 .. NP-1 and the loss as NP ----
+__device__ __forceinline__ float* ws_red(const WsShared& S) { return S.bufs; }
+__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.bufs + WS_CONS * 32 * 160; }
+__device__ __forceinline__ void ws_park_producer(const WsShared& S, const float (&g3)[HID + 1], float loss) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* red3 = ws_red3(S);
+    loss = warp_sum(loss);
+    if (lane == 0) red3[warp * (HID + 2) + HID + 1] = loss;
+#pragma unroll
+    for (int j = 0; j <= HID; ++j) {
+        const float s = warp_sum(g3[j]);
+        if (lane == 0) red3[warp * (HID + 2) + j] = s;
+    }
+}
+__device__ __forceinline__ void ws_park_consumer(const WsShared& S, int cw, const f2 (&acc)[80]) {
+    const int lane = threadIdx.x & 31;
+    float4* dst = reinterpret_cast<float4*>(ws_red(S) + (cw * 32 + lane) * 160);
+#pragma unroll
+    for (int e = 0; e < 40; ++e) {
+        float4 v;
+        unpack2(acc[2 * e], v.x, v.y);
+        unpack2(acc[2 * e + 1], v.z, v.w);
+        dst[e] = v;
+    }
+}
+template <int DIN, class ST>
+__device__ __forceinline__ void ws_cta_sums(const WsShared& S, ST store) {
+    constexpr int NP = param_count(DIN, 1);
+    const float* red = ws_red(S);
+    const float* red3 = ws_red3(S);
+    for (int qi = threadIdx.x; qi < 5 * 160; qi += WS_THREADS) {
+        const int t = qi / 160, e = qi % 160;
+        const int idx = ws_tile_param<DIN>(t, e / 20, e % 20);
+        if (idx >= 0) {
+            float s = 0.f;
+            for (int c = 0; c < WS_CONS; ++c)
+#pragma unroll
+                for (int g = 0; g < WS_NG; ++g) s += red[(c * 32 + g * 5 + t) * 160 + e];
+            store(idx, s);
+        }
+    }
+    if (threadIdx.x <= HID) {
+        float s = 0.f;
+        for (int w = 0; w < 4 * WS_GROUPS; ++w) s += red3[w * (HID + 2) + threadIdx.x];
+        store((threadIdx.x < HID ? off_W3(DIN) : off_b3(DIN, 1) - HID) + threadIdx.x, s);
+    }
+    if (threadIdx.x == 32) {
+        float s = 0.f;
+        for (int w = 0; w < 4 * WS_GROUPS; ++w) s += red3[w * (HID + 2) + HID + 1];
+        store(NP, s);
+    }
+}
+constexpr int WS_BAR_A = 8, WS_BAR_B = 9, WS_BAR_C = 10, WS_BAR_D = 11;             // CTA-wide named barriers (both roles, any code location)
+
+// =====================================================================================================================
+// one-shot kernel (rcmarl_grad): one sweep, sums to the CTA's partial slot
+// =====================================================================================================================
+template <int NA, int DIN>
+__device__ __forceinline__ void ws_body(const GradParams& P, const rcmarl_grad_job& job, float* smem, int y, int gy) {
+    static_assert(NA == 5, "instantiated for n_agents = 5 (operand widths 16 / 24)");
+    constexpr int NP = param_count(DIN, 1);
+    rcmarl_rows Rw = P.rows;
+    if (job.time_idx) Rw.time_idx = job.time_idx;
+    const int warp = threadIdx.x >> 5;
+    const WsShared S = ws_carve(smem);
+    ws_init(S);
+    pdl_wait();
+    stage_weights(S.sw, job.w, NP);
+    __syncthreads();
+    ws_build_operands<DIN>(S);
+    __syncthreads();
+    tmem_fence_after_sync();
+    const int nq = ws_tile_count(Rw.n_rows, y, gy);
+    float* out = P.partial + (int64_t)blockIdx.x * P.stride;
+    if (warp < 4 * WS_GROUPS) {
+        reg_dec<WS_REGS_PROD>();
+        uint32_t mph = 0;
+        float g3[HID + 1];
+#pragma unroll
+        for (int j = 0; j <= HID; ++j) g3[j] = 0.f;
+        float loss = 0.f;
+        ws_produce<NA, DIN>(S, Rw, job, y, gy, nq, 0u, mph, g3, loss);
+        named_barrier(WS_BAR_A, WS_THREADS);                          // every tile produced and consumed
+        ws_park_producer(S, g3, loss);
+    } else {
+        reg_inc<WS_REGS_CONS>();
+        const int cw = warp - 4 * WS_GROUPS;
+        f2 acc[80];                                                   // 8 (a) x 20 (delta), packed as pairs over the delta index
+#pragma unroll
+        for (int e = 0; e < 80; ++e) acc[e] = pack2(0.f, 0.f);
+        ws_consume(S, cw, nq, 0u, acc);
+        named_barrier(WS_BAR_A, WS_THREADS);
+        ws_park_consumer(S, cw, acc);
+    }
+#if RCMARL_PDL_REDUCE
+    pdl_launch_dependents();
+#endif
+    __syncthreads();                                                  // (B) scratch complete
+    ws_cta_sums<DIN>(S, [out](int i, float v) { out[i] = v; });
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_all(*S.tslot);
+}
+
+// scalar-output nets at n_agents = 5 (mean-squared-error jobs); everything else stays on grad_kernel
+__global__ void __launch_bounds__(WS_THREADS, 1) grad_kernel_ws(const __grid_constant__ GradParams P) {
+    extern __shared__ __align__(16) float smem[];
+    int j = 0;
+    while (j + 1 < P.n_jobs && (int)blockIdx.x >= P.cta_first[j + 1]) ++j;
+    const rcmarl_grad_job& job = P.jobs[j];
+    const int y = (int)blockIdx.x - P.cta_first[j], gy = P.cta_first[j + 1] - P.cta_first[j];
+    if (job.kind == RCMARL_IN_SA) ws_body<5, 15>(P, job, smem, y, gy);
+    else ws_body<5, 10>(P, job, smem, y, gy);
+}
+
+}  // namespace rcmarl

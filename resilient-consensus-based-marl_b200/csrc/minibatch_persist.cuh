@@ -20,6 +20,12 @@
 #pragma once
 #include "grad_kernel.cuh"
 #include "comm.cuh"
+#ifndef RCMARL_GRAD_WS
+#define RCMARL_GRAD_WS 0
+#endif
+#if RCMARL_GRAD_WS
+#include "grad_kernel_ws.cuh"
+#endif
 
 namespace rcmarl {
 
@@ -145,5 +151,148 @@ mb_persist_kernel(const __grid_constant__ MbParams P) {
     if (ch.kind == RCMARL_IN_SA) mb_body<NA, 3 * NA, NW>(P, ch, j, smem, y, gy);
     else mb_body<NA, 2 * NA, NW>(P, ch, j, smem, y, gy);
 }
+
+#if RCMARL_GRAD_WS
+// =====================================================================================================================
+// The same persistent fit on the warp-specialised tensor-core core (grad_kernel_ws.cuh), n_agents = 5.  Both roles run the
+// whole step loop inside their own branch (the register budgets of producers and consumers differ after setmaxnreg, so
+// there is no common code after the split); CTA-wide points are named barriers that both roles reach.
+// =====================================================================================================================
+struct MbStepCtx {
+    uint2* my1;                 // this CTA's level-1 cells
+    const uint2* chain1;        // level-1 cells of the chain's first CTA
+    const CommDev* comm;
+    int64_t off2;               // the chain's block in the level-2 cells
+    int32_t gy, stride, sl_begin, sl_end, S, sgroup, e_local, e_per_warp;
+    float loss_coef;
+};
+
+// sums of this step -> level-1 cells -> slice owner's CTA-ordered sum -> level-2 cells -> SGD step on the shared-memory copy
+template <int DIN>
+__device__ __forceinline__ void mb_step_tail(const WsShared& S, const MbStepCtx& c, uint32_t s1, uint32_t s2, float coef,
+                                             bool first_epoch, float& loss_acc) {
+    constexpr int NP = param_count(DIN, 1);
+    const int warp = threadIdx.x >> 5;
+    uint2* my1 = c.my1;
+    ws_cta_sums<DIN>(S, [my1, s1](int i, float v) { st_cell(my1 + i, v, s1); });
+    for (int base = c.sl_begin + warp * c.e_per_warp; base < c.sl_end; base += WS_WARPS * c.e_per_warp) {
+        const int i = base + c.e_local;
+        float s = 0.f;
+        if (i < c.sl_end) {
+            for (int yy = c.sgroup; yy < c.gy; yy += c.S)
+                s += __uint_as_float(poll_cell(c.chain1 + (int64_t)yy * c.stride + i, s1, c.comm->error).x);
+        }
+        for (int o = 1; o < c.S; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (i < c.sl_end && c.sgroup == 0) comm_push(*c.comm, c.off2 + i, s, s2);
+    }
+    for (int i = threadIdx.x; i <= NP; i += WS_THREADS) {
+        const float tot = comm_wait_total(*c.comm, c.off2 + i, s2);
+        if (i < NP) S.sw[i] = S.sw[i] - coef * tot;
+        else if (first_epoch) loss_acc += c.loss_coef * tot;
+    }
+}
+
+template <int NA, int DIN>
+__device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch, int j, float* smem, int y, int gy) {
+    constexpr int NP = param_count(DIN, 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WsShared S = ws_carve(smem);
+    ws_init(S);
+    pdl_wait();
+    stage_weights(S.sw, ch.w, NP);
+    __syncthreads();
+
+    rcmarl_grad_job gj;
+    gj.w = ch.w; gj.target = ch.target; gj.sums = nullptr; gj.time_idx = nullptr;
+    gj.target_stride = ch.target_stride; gj.kind = ch.kind; gj.action_agent = 0;
+    rcmarl_rows Rw = P.rows;
+
+    MbStepCtx c;
+    c.my1 = P.cells1 + (int64_t)blockIdx.x * P.stride;
+    c.chain1 = P.cells1 + (int64_t)P.cta_first[j] * P.stride;
+    c.comm = &P.comm;
+    c.off2 = (int64_t)j * P.stride;
+    c.gy = gy; c.stride = P.stride;
+    const int per = (NP + 1 + gy - 1) / gy;
+    c.sl_begin = y * per < NP + 1 ? y * per : NP + 1;
+    c.sl_end = c.sl_begin + per < NP + 1 ? c.sl_begin + per : NP + 1;
+    int Sl = 1;
+    while (Sl < gy && Sl < 32) Sl <<= 1;
+    c.S = Sl; c.sgroup = lane & (Sl - 1); c.e_local = lane / Sl; c.e_per_warp = 32 / Sl;
+    c.loss_coef = ch.loss_coef;
+    const int nb = (P.n_times + P.mb_times - 1) / P.mb_times;
+    const float world = (float)P.comm.world;
+    uint32_t seq1 = P.seq1, seq2 = P.comm.seq, qbase = 0;
+    float loss_acc = 0.f;
+
+    if (warp < 4 * WS_GROUPS) {
+        reg_dec<WS_REGS_PROD>();
+        uint32_t mph = 0;
+        for (int e = 0; e < P.epochs; ++e) {
+            for (int b = 0; b < nb; ++b, ++seq1, ++seq2) {
+                ws_build_operands<DIN>(S);
+                named_barrier(WS_BAR_C, WS_THREADS);
+                tmem_fence_after_sync();
+                const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
+                Rw.n_rows = (int64_t)cnt * Rw.n_envs;
+                Rw.time_idx = ch.time_idx + (int64_t)e * P.n_times + (int64_t)b * P.mb_times;
+                const int nq = ws_tile_count(Rw.n_rows, y, gy);
+                float g3[HID + 1];
+#pragma unroll
+                for (int k = 0; k <= HID; ++k) g3[k] = 0.f;
+                float loss = 0.f;
+                ws_produce<NA, DIN>(S, Rw, gj, y, gy, nq, qbase, mph, g3, loss);
+                qbase += (uint32_t)nq;
+                named_barrier(WS_BAR_A, WS_THREADS);
+                ws_park_producer(S, g3, loss);
+                named_barrier(WS_BAR_B, WS_THREADS);
+                mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / ((float)Rw.n_rows * world), e == 0, loss_acc);
+                named_barrier(WS_BAR_D, WS_THREADS);                  // new parameters visible; scratch reusable
+            }
+        }
+    } else {
+        reg_inc<WS_REGS_CONS>();
+        const int cw = warp - 4 * WS_GROUPS;
+        for (int e = 0; e < P.epochs; ++e) {
+            for (int b = 0; b < nb; ++b, ++seq1, ++seq2) {
+                ws_build_operands<DIN>(S);
+                named_barrier(WS_BAR_C, WS_THREADS);
+                tmem_fence_after_sync();
+                const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
+                Rw.n_rows = (int64_t)cnt * Rw.n_envs;
+                const int nq = ws_tile_count(Rw.n_rows, y, gy);
+                f2 acc[80];
+#pragma unroll
+                for (int k = 0; k < 80; ++k) acc[k] = pack2(0.f, 0.f);
+                ws_consume(S, cw, nq, qbase, acc);
+                qbase += (uint32_t)nq;
+                named_barrier(WS_BAR_A, WS_THREADS);
+                ws_park_consumer(S, cw, acc);
+                named_barrier(WS_BAR_B, WS_THREADS);
+                mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / ((float)Rw.n_rows * world), e == 0, loss_acc);
+                named_barrier(WS_BAR_D, WS_THREADS);
+            }
+        }
+    }
+    if (y == 0) {
+        for (int i = threadIdx.x; i < NP; i += WS_THREADS) ch.w[i] = S.sw[i];
+        if (threadIdx.x == (NP % WS_THREADS) && ch.loss_out) *ch.loss_out = ch.loss_accumulate ? *ch.loss_out + loss_acc : loss_acc;
+    }
+    tmem_fence_before_sync();
+    named_barrier(WS_BAR_C, WS_THREADS);
+    if (warp == 0) tmem_dealloc_all(*S.tslot);
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) mb_persist_ws_kernel(const __grid_constant__ MbParams P) {
+    extern __shared__ __align__(16) float smem[];
+    pdl_launch_dependents();
+    int j = 0;
+    while (j + 1 < P.n_chains && (int)blockIdx.x >= P.cta_first[j + 1]) ++j;
+    const MbChain& ch = P.chains[j];
+    const int y = (int)blockIdx.x - P.cta_first[j], gy = P.cta_first[j + 1] - P.cta_first[j];
+    if (ch.kind == RCMARL_IN_SA) mb_body_ws<5, 15>(P, ch, j, smem, y, gy);
+    else mb_body_ws<5, 10>(P, ch, j, smem, y, gy);
+}
+#endif  // RCMARL_GRAD_WS
 
 }  // namespace rcmarl

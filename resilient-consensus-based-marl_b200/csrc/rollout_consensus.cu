@@ -111,65 +111,92 @@ __device__ __forceinline__ void push_group8(Track<H>& t, float (&g)[8]) {
 
 constexpr int CM_UNROLL = 8;
 
-template <int H>
-__global__ void __launch_bounds__(256) clip_mean_vec4_kernel(const float* __restrict__ vals, int n, int64_t P4,
-                                                             int64_t row_stride, float* __restrict__ out) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 column
-    if (c >= P4) return;
-    Track<H> t[4];
+// VEC consecutive columns of one neighbour row as one streaming load (16 or 8 bytes per lane, read-only path, no L1 fill)
+template <int VEC>
+__device__ __forceinline__ void ld_stream_vec(const float* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 r = ld_stream(reinterpret_cast<const float4*>(p));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    } else {
+        static_assert(VEC == 2, "vector width");
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+    }
+}
+
+// One thread owns VEC adjacent columns.  VEC = 4 (16-byte loads) for H <= 1, where a column costs a handful of registers;
+// VEC = 2 for H >= 2: the per-column state (2 (H + 1) order statistics + the 8-row group being sorted) is what limits
+// occupancy there (round 1: 98 registers, 22 % occupancy, DRAM 55 % busy with the ALUs 45 % busy -- neither saturated, the
+// loads of a thread's next row group simply were not in flight while it sorted the current one), and half the columns per
+// thread doubles the resident warps that cover each other's load latency.  8-byte loads still fill whole 32-byte sectors.
+template <int H, int VEC>
+__global__ void __launch_bounds__(256) clip_mean_vec_kernel(const float* __restrict__ vals, int n, int64_t PV,
+                                                            int64_t row_stride, float* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // vector column
+    if (c >= PV) return;
+    Track<H> t[VEC];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) t[q].init();
-    const float4* base = reinterpret_cast<const float4*>(vals) + c;
-    const int64_t rs4 = row_stride >> 2;
-    float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < VEC; ++q) t[q].init();
+    const float* base = vals + c * VEC;
+    float own[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) own[q] = 0.f;
     int k = 0;
     for (; k + CM_UNROLL <= n; k += CM_UNROLL) {
-        float4 v[CM_UNROLL];
+        float v[CM_UNROLL][VEC];
 #pragma unroll
-        for (int u = 0; u < CM_UNROLL; ++u) v[u] = ld_stream(base + (int64_t)(k + u) * rs4);
-        if (k == 0) own = v[0];
+        for (int u = 0; u < CM_UNROLL; ++u) ld_stream_vec<VEC>(base + (int64_t)(k + u) * row_stride, v[u]);
+        if (k == 0) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) own[q] = v[0][q];
+        }
         if constexpr (H >= 2) {
-            float g[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = v[u].x;
-            push_group8<H>(t[0], g);
+            for (int q = 0; q < VEC; ++q) {
+                float g[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = v[u].y;
-            push_group8<H>(t[1], g);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = v[u].z;
-            push_group8<H>(t[2], g);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = v[u].w;
-            push_group8<H>(t[3], g);
+                for (int u = 0; u < 8; ++u) g[u] = v[u][q];
+                push_group8<H>(t[q], g);
+            }
         } else {
 #pragma unroll
-            for (int u = 0; u < CM_UNROLL; ++u) { t[0].push(v[u].x); t[1].push(v[u].y); t[2].push(v[u].z); t[3].push(v[u].w); }
+            for (int u = 0; u < CM_UNROLL; ++u)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) t[q].push(v[u][q]);
         }
     }
     for (; k < n; ++k) {
-        float4 v = ld_stream(base + (int64_t)k * rs4);
-        if (k == 0) own = v;
-        t[0].push(v.x); t[1].push(v.y); t[2].push(v.z); t[3].push(v.w);
-    }
-    float lo[4], hi[4];
-    t[0].window(own.x, lo[0], hi[0]); t[1].window(own.y, lo[1], hi[1]);
-    t[2].window(own.z, lo[2], hi[2]); t[3].window(own.w, lo[3], hi[3]);
-    float4 r;
-    if (t[0].identity_ok(lo[0], hi[0]) && t[1].identity_ok(lo[1], hi[1]) && t[2].identity_ok(lo[2], hi[2]) &&
-        t[3].identity_ok(lo[3], hi[3])) {
-        r.x = t[0].finish(lo[0], hi[0], n); r.y = t[1].finish(lo[1], hi[1], n);
-        r.z = t[2].finish(lo[2], hi[2], n); r.w = t[3].finish(lo[3], hi[3], n);
-    } else {                                   // outlier column(s): second pass, clip first, then sum (reference order)
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        for (int kk = 0; kk < n; ++kk) {
-            const float4 v = ld_stream(base + (int64_t)kk * rs4);
-            s0 += clip1(v.x, lo[0], hi[0]); s1 += clip1(v.y, lo[1], hi[1]);
-            s2 += clip1(v.z, lo[2], hi[2]); s3 += clip1(v.w, lo[3], hi[3]);
+        float v[VEC];
+        ld_stream_vec<VEC>(base + (int64_t)k * row_stride, v);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            if (k == 0) own[q] = v[q];
+            t[q].push(v[q]);
         }
-        r.x = s0 / (float)n; r.y = s1 / (float)n; r.z = s2 / (float)n; r.w = s3 / (float)n;
     }
-    reinterpret_cast<float4*>(out)[c] = r;
+    float lo[VEC], hi[VEC], r[VEC];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        t[q].window(own[q], lo[q], hi[q]);
+        ok = ok && t[q].identity_ok(lo[q], hi[q]);
+    }
+    if (ok) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) r[q] = t[q].finish(lo[q], hi[q], n);
+    } else {                                   // outlier column(s): second pass, clip first, then sum (reference order)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) r[q] = 0.f;
+        for (int kk = 0; kk < n; ++kk) {
+            float v[VEC];
+            ld_stream_vec<VEC>(base + (int64_t)kk * row_stride, v);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) r[q] += clip1(v[q], lo[q], hi[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) r[q] = r[q] / (float)n;
+    }
+    if constexpr (VEC == 4) reinterpret_cast<float4*>(out)[c] = make_float4(r[0], r[1], r[2], r[3]);
+    else reinterpret_cast<float2*>(out)[c] = make_float2(r[0], r[1]);
 }
 
 template <int H>
@@ -198,10 +225,11 @@ __global__ void __launch_bounds__(256) clip_mean_scalar_kernel(const float* __re
 
 template <int H>
 static int launch_clip_mean(const float* vals, int n, int64_t P, int64_t row_stride, float* out, cudaStream_t st) {
-    const bool vec = (P % 4 == 0) && (row_stride % 4 == 0) && ((uintptr_t)vals % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    constexpr int VEC = H >= 2 ? 2 : 4;
+    const bool vec = (P % VEC == 0) && (row_stride % VEC == 0) && ((uintptr_t)vals % (4 * VEC) == 0) && ((uintptr_t)out % (4 * VEC) == 0);
     if (vec) {
-        const int64_t P4 = P / 4;
-        clip_mean_vec4_kernel<H><<<(unsigned)((P4 + 255) / 256), 256, 0, st>>>(vals, n, P4, row_stride, out);
+        const int64_t PV = P / VEC;
+        clip_mean_vec_kernel<H, VEC><<<(unsigned)((PV + 255) / 256), 256, 0, st>>>(vals, n, PV, row_stride, out);
     } else {
         clip_mean_scalar_kernel<H><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(vals, n, P, row_stride, out);
     }

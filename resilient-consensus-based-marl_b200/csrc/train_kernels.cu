@@ -36,6 +36,13 @@
 #if RCMARL_GRAD_TC
 #include "grad_kernel_tc.cuh"
 #endif
+// RCMARL_GRAD_WS=1 (make variant_v7): mean-squared-error jobs at n_agents = 5 run on the warp-specialised tensor-core kernel
+#ifndef RCMARL_GRAD_WS
+#define RCMARL_GRAD_WS 0
+#endif
+#if RCMARL_GRAD_WS
+#include "grad_kernel_ws.cuh"
+#endif
 #include "comm.cuh"
 #include "minibatch_persist.cuh"
 
@@ -494,7 +501,19 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
         cfg.blockDim = dim3(32 * NWC);
         cfg.dynamicSmemBytes = smem_ce;
         RC_CUDA(cudaLaunchKernelEx(&cfg, RC_GRAD_KERNEL<NA, RCMARL_LOSS_CE>, P));
-#if RCMARL_GRAD_TC
+#if RCMARL_GRAD_WS
+    } else if (NA == 5) {
+        constexpr size_t smem_ws = sizeof(float) * ws_smem_floats();
+        static_assert(smem_ws <= 227 * 1024, "grad_kernel_ws exceeds the shared-memory limit");
+        static bool attr_ws = false;
+        if (!attr_ws) {
+            if (set_smem(grad_kernel_ws, smem_ws)) return RCMARL_ERR_CUDA;
+            attr_ws = true;
+        }
+        cfg.blockDim = dim3(WS_THREADS);
+        cfg.dynamicSmemBytes = smem_ws;
+        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel_ws, P));
+#elif RCMARL_GRAD_TC
     } else if (NA == 5) {
         constexpr size_t smem_tc = sizeof(float) * (grad_tc_smem_floats<15>() > grad_tc_smem_floats<10>()
                                                         ? grad_tc_smem_floats<15>() : grad_tc_smem_floats<10>());
@@ -523,7 +542,9 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
 // chunks (64 rows) one CTA of this configuration consumes per sweep
 template <int NA>
 static int grad_chunks_per_cta(int loss_mode) {
-#if RCMARL_GRAD_TC
+#if RCMARL_GRAD_WS
+    if (NA == 5 && loss_mode == RCMARL_LOSS_MSE) return 2;      // one 128-row tile (= two 64-row chunks) at a time
+#elif RCMARL_GRAD_TC
     if (NA == 5 && loss_mode == RCMARL_LOSS_MSE) return 4;      // two 128-row tiles (= four 64-row chunks) per CTA and round
 #endif
     return loss_mode == RCMARL_LOSS_CE ? RC_GRAD_WARPS<NA, RCMARL_LOSS_CE>() : RC_GRAD_WARPS<NA, RCMARL_LOSS_MSE>();
@@ -637,6 +658,33 @@ static int grad_job_cost(int na, int kind, int loss_mode) {
     if (loss_mode == RCMARL_LOSS_CE) return grad_row_cost(2 * na, NACT);
     return grad_row_cost(kind == RCMARL_IN_SA ? 3 * na : 2 * na, 1);
 }
+
+#if RCMARL_GRAD_WS
+static int launch_mb_persist_ws(const MbParams& P, int n_ctas, cudaStream_t st) {
+    constexpr size_t smem = sizeof(float) * ws_smem_floats();
+    static int resident = -1;
+    if (resident < 0) {
+        if (set_smem(mb_persist_ws_kernel, smem)) return RCMARL_ERR_CUDA;
+        int per_sm = 0;
+        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_persist_ws_kernel, WS_THREADS, smem));
+        resident = per_sm * sm_count_cached();
+    }
+    if (n_ctas > resident) return RCMARL_ERR_ARG;
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(WS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = &pdl;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, mb_persist_ws_kernel, P));
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+#endif
 
 template <int NA>
 static int launch_mb_persist(const MbParams& P, int n_ctas, cudaStream_t st) {
@@ -895,6 +943,9 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
         P.comm.rank = 0; P.comm.world = 1; P.comm.seq = seq_first;
     }
     cudaStream_t st = (cudaStream_t)stream;
+#if RCMARL_GRAD_WS
+    if (NA == 5) return launch_mb_persist_ws(P, n_ctas, st);
+#endif
     return NA == 5 ? launch_mb_persist<5>(P, n_ctas, st) : launch_mb_persist<16>(P, n_ctas, st);
 }
 

@@ -45,11 +45,14 @@ class Trainer:
         self.N, self.nrow, self.ncol = int(n_envs), int(nrow), int(ncol)
         self.gamma, self.mu = float(gamma), float(mu)
         # per-agent trimming parameter H and fast learning rate (agents/resilient_CAC_agents.py:28-36 stores both per agent)
-        self.H = [int(H)] * NA if np.isscalar(H) else [int(x) for x in H]
-        self.fast_lr = [float(fast_lr)] * NA if np.isscalar(fast_lr) else [float(x) for x in fast_lr]
-        if len(self.H) != NA or len(self.fast_lr) != NA:
+        n_real = self.n_real
+        self.H = [int(H)] * n_real if np.isscalar(H) else [int(x) for x in H]
+        self.fast_lr = [float(fast_lr)] * n_real if np.isscalar(fast_lr) else [float(x) for x in fast_lr]
+        if len(self.H) != n_real or len(self.fast_lr) != n_real:
             raise L.RcmarlError("H / fast_lr must be scalars or one value per agent")
-        self.slow_lr = [float(slow_lr)] * NA if np.isscalar(slow_lr) else [float(x) for x in slow_lr]
+        self.H += [0] * (NA - n_real)
+        self.fast_lr += [self.fast_lr[0]] * (NA - n_real)
+        self.slow_lr = [float(slow_lr)] * NA if np.isscalar(slow_lr) else [float(x) for x in slow_lr] + [0.0] * (NA - n_real)
         self.max_ep_len, self.n_ep_fixed, self.n_epochs = int(max_ep_len), int(n_ep_fixed), int(n_epochs)
         self.block = self.max_ep_len * self.n_ep_fixed                    # time rows per fixed-policy block
         self.buffer_size = int(buffer_size)                               # in time rows (train_agents.py:158)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, GPU call 7: v7 with LDS/STS (shared address space kept), nanosleep back-off, unpredicated consumer body
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+P=$PWD/resilient-consensus-based-marl_b200/rcmarl
+mkdir -p gpurun_out
+echo "== grad timing: default, v7"
+timeout 200 python tools/ab_grad.py dump gpurun_out/ab_base.npz 2>&1 | grep -E "TIMING|rror"
+RCMARL_LIB=$P/librcmarl_v7.so timeout 200 python tools/ab_grad.py dump gpurun_out/ab_v7.npz 2>&1 | grep -E "TIMING|rror|rap" | tail -4
+python tools/ab_grad.py cmp gpurun_out/ab_base.npz gpurun_out/ab_v7.npz | tail -3
+echo "== v7: tests"
+RCMARL_LIB=$P/librcmarl_v7.so timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_trainer_gpu.py tests/test_benchshape_parity_gpu.py -m gpu -q 2>&1 | tail -5
+echo "== ncu v7"
+RCMARL_LIB=$P/librcmarl_v7.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:grad_kernel_ws -s 2 -c 1 -o gpurun_out/prof_v7c python tools/prof_grad.py 4096000 8 3 2>&1 | tail -1
+echo "== bench with v7 (short)"
+RCMARL_LIB=$P/librcmarl_v7.so timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-consensus 2>/dev/null | python -c "import sys, json; d = json.loads(sys.stdin.read()); print('BENCH v7', d['value'], d['ms_per_step'], json.dumps(d['roofline']['regimes']), json.dumps(d['breakdown_ms']))"
