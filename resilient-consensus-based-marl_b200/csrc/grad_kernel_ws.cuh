@@ -19,7 +19,7 @@
 //       sum over the buffer's rows of the outer products [x | 1] (x) delta1 and [h1 | 1] (x) delta2 as 8 x 20 register
 //       tiles (5 tiles x 6 row groups per warp; 7 LDS.128 per 80 FFMA2), accumulated across ALL tiles of the CTA.
 //   Buffers are handed over with full / empty mbarriers; tile q goes to producer group q % 2, buffer q % WS_NBUF and
-//   consumer q % 4 (static, so every sum keeps a fixed order: results are bitwise reproducible).
+//   consumer team q % 2 (static, so every sum keeps a fixed order: results are bitwise reproducible).
 // While a producer group waits for its MMAs the other group and the consumers own the issue slots; the MMAs themselves
 // run beside the FMA pipes.
 #pragma once
@@ -31,16 +31,28 @@ namespace rcmarl {
 #define RCMARL_WS_GROUPS 2
 #endif
 constexpr int WS_GROUPS = RCMARL_WS_GROUPS;                   // producer groups of 4 warps (2 or 3)
-constexpr int WS_CONS = 4;                                    // consumer warps
+constexpr int WS_CONS = 8;                                    // consumer warps (two per scheduler), in two teams of four
 constexpr int WS_WARPS = 4 * WS_GROUPS + WS_CONS;             // 12
 constexpr int WS_THREADS = 32 * WS_WARPS;                     // 384
-constexpr int WS_NBUF = 5;                                    // tile buffers in the ring
-constexpr int WS_ROWF = 76;                                   // floats per buffer row: x 16 | h1 20 | delta1 20 | delta2 20
-constexpr int WS_OX = 0, WS_OH1 = 16, WS_OD1 = 36, WS_OD2 = 56;
+constexpr int WS_RING = 2;                                    // tile buffers per stream (producer group g <-> consumer team g)
+constexpr int WS_NBUF = WS_RING * WS_GROUPS;                  // 4: each stream owns its own ring -- the uses of a buffer are then
+                                                              // strictly ordered by ONE producer / consumer pair, which the
+                                                              // parity waits of the mbarriers need (a shared ring let one stream
+                                                              // run two uses ahead of the other and alias the parity)
+// floats per buffer row: x 16 | h1 20 + [1 0 0 0] | delta1 as two halves of 10 + 2 pad | delta2 likewise | 4 pad.
+// Every consumer operand is then a run of aligned LDS.128 (2 for an a-tile, 3 for a delta half) with no selects; 92 floats =
+// 23 x 16 bytes (odd), so the row-per-thread STS.128 of the producers and the row-group reads of the consumers spread over
+// the banks.
+constexpr int WS_ROWF = 92;
+constexpr int WS_OX = 0, WS_OH1 = 16, WS_OD1 = 40, WS_OD2 = 64, WS_DHALF = 12;
 constexpr int WS_TILE_ROWS = 128;
-constexpr int WS_NG = 6;                                      // row groups per consumer warp (5 tiles x 6 groups = 30 lanes)
-// setmaxnreg targets (multiples of 8): 2 groups: 256 x 128 + 128 x 240 = 63 488 registers; 3 groups: 384 x 96 + 128 x 216 = 64 512
-constexpr int WS_REGS_PROD = WS_GROUPS == 2 ? 128 : 96, WS_REGS_CONS = WS_GROUPS == 2 ? 240 : 216;
+constexpr int WS_NG = 3;                                      // row groups per consumer warp (5 a-tiles x 2 delta halves x 3 = 30 lanes)
+constexpr int WS_TEAM = 4;                                    // consumer warps that share one tile
+constexpr int WS_ACC = 40;                                    // packed accumulator pairs per lane: 8 (a) x 10 (half of delta)
+// 16 warps x 32 lanes x 128 registers = the whole register file: no setmaxnreg needed (the first versions ran 4 consumer
+// warps with 8 x 20 tiles at 240 registers; one FFMA2 stream per scheduler issued only ~30 % of the cycles, and the consumers
+// were the bottleneck -- two narrower consumer warps per scheduler cover each other's latencies)
+constexpr int WS_REGS_PROD = 128, WS_REGS_CONS = 128;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -84,18 +96,18 @@ __device__ __forceinline__ void ws_store_operand(uint32_t tlane, int col_hi, int
         uint32_t h[8], l[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float hv = to_tf32(v[8 * c + k]);
-            h[k] = __float_as_uint(hv);
-            l[k] = __float_as_uint(v[8 * c + k] - hv);
+            // round-to-nearest (ties away) to 10 mantissa bits, as cvt.rna.tf32.f32 without its inf / NaN guard: 2 integer ops
+            h[k] = (__float_as_uint(v[8 * c + k]) + 0x1000u) & 0xFFFFE000u;
+            l[k] = __float_as_uint(v[8 * c + k] - __uint_as_float(h[k]));
         }
         tmem_st8(tlane + col_hi + 8 * c, h);
         tmem_st8(tlane + col_lo + 8 * c, l);
     }
 }
 
-constexpr int ws_smem_floats() {
-    // packed net | alignment slack | B operands (hi + lo of 32x16, 32x24, 32x24) | tile buffers | barriers + tmem slot
-    return round32(param_count(15, 1)) + 32 + 2 * TC_N * 16 + 4 * TC_N * 24 + WS_NBUF * WS_TILE_ROWS * WS_ROWF + 64;
+constexpr int ws_smem_floats(int n_slots = 1) {
+    // packed net(s) | alignment slack | B operands (hi + lo of 32x16, 32x24, 32x24) | tile buffers | barriers + tmem slot
+    return n_slots * round32(param_count(15, 1)) + 32 + 2 * TC_N * 16 + 4 * TC_N * 24 + WS_NBUF * WS_TILE_ROWS * WS_ROWF + 64;
 }
 
 // packed-parameter index of element (ii, j) of consumer tile t (a rows 8 t .. 8 t + 7 of [x | 1] for t < 2, of [h1 | 1] else)
@@ -109,25 +121,32 @@ __device__ __forceinline__ int ws_tile_param(int t, int ii, int j) {
     return i < HID ? off_W2(DIN) + i * HID + j : (i == HID ? off_b2(DIN) + j : -1);
 }
 
-// consumer: acc[8][20] += a (x) delta for one buffer row (7 LDS.128, 80 FFMA2 with a broadcast scalar operand)
-__device__ __forceinline__ void ws_consume_row(const float* __restrict__ rp, int acol, int dcol, bool last_tile, f2 (&acc)[80]) {
+// consumer: acc[8][10] += a (x) delta-half for one buffer row (5 LDS.128, 40 FFMA2 with a broadcast scalar operand)
+__device__ __forceinline__ void ws_consume_row(const float* __restrict__ rp, int acol, int dcol, f2 (&acc)[WS_ACC]) {
     const float4 a0 = *reinterpret_cast<const float4*>(rp + acol);
-    float4 a1 = *reinterpret_cast<const float4*>(rp + acol + 4);
-    if (last_tile) a1 = make_float4(1.f, 0.f, 0.f, 0.f);
-    f2 d[10];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(rp + dcol + 4 * k);
-        d[2 * k] = pack2(v.x, v.y);
-        d[2 * k + 1] = pack2(v.z, v.w);
-    }
+    const float4 a1 = *reinterpret_cast<const float4*>(rp + acol + 4);
+    const float4 d0 = *reinterpret_cast<const float4*>(rp + dcol);
+    const float4 d1 = *reinterpret_cast<const float4*>(rp + dcol + 4);
+    const float4 d2 = *reinterpret_cast<const float4*>(rp + dcol + 8);
+    const f2 d[5] = {pack2(d0.x, d0.y), pack2(d0.z, d0.w), pack2(d1.x, d1.y), pack2(d1.z, d1.w), pack2(d2.x, d2.y)};
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
         const f2 aa = pack2(a[ii], a[ii]);
 #pragma unroll
-        for (int jp = 0; jp < 10; ++jp) acc[ii * 10 + jp] = fma2(aa, d[jp], acc[ii * 10 + jp]);
+        for (int jp = 0; jp < 5; ++jp) acc[ii * 5 + jp] = fma2(aa, d[jp], acc[ii * 5 + jp]);
     }
+}
+
+// a 20-vector as two halves of 10 values + 2 zeros each (the consumers' delta operands)
+template <int N>
+__device__ __forceinline__ void ws_store_halves(float* p, const float (&d)[N]) {
+    st4(p, d[0], d[1], d[2], d[3]);
+    st4(p + 4, d[4], d[5], d[6], d[7]);
+    st4(p + 8, d[8], d[9], 0.f, 0.f);
+    st4(p + 12, d[10], d[11], d[12], d[13]);
+    st4(p + 16, d[14], d[15], d[16], d[17]);
+    st4(p + 20, d[18], d[19], 0.f, 0.f);
 }
 
 // inputs of row r of tile q of this CTA: features, target, and whether the row exists
@@ -147,8 +166,9 @@ struct WsShared {
     uint64_t *full, *empty, *mma_bar;
     uint32_t* tslot;
 };
-__device__ __forceinline__ WsShared ws_carve(float* smem) {
-    constexpr int NPMAX = param_count(15, 1);
+constexpr int WS_SLOT = round32(param_count(15, 1));                // floats per parameter slot (768)
+__device__ __forceinline__ WsShared ws_carve(float* smem, int n_slots = 1) {
+    const int NPMAX = (n_slots - 1) * WS_SLOT + param_count(15, 1);
     WsShared S;
     S.sw = smem;
     // 128-byte alignment by OFFSET arithmetic on the shared-memory pointer: a round trip through uintptr_t would make every
@@ -163,7 +183,7 @@ __device__ __forceinline__ WsShared ws_carve(float* smem) {
     S.bufs = S.b3l + TC_N * 24;                                       // [WS_NBUF][128][WS_ROWF]
     uint64_t* bars = reinterpret_cast<uint64_t*>(S.bufs + WS_NBUF * WS_TILE_ROWS * WS_ROWF);
     S.full = bars;                                                    // [WS_NBUF]  producers -> consumer (4 warp arrivals)
-    S.empty = bars + WS_NBUF;                                         // [WS_NBUF]  consumers -> producers (WS_CONS arrivals)
+    S.empty = bars + WS_NBUF;                                         // [WS_NBUF]  consumer team -> producers (WS_TEAM arrivals)
     S.mma_bar = bars + 2 * WS_NBUF;                                   // [WS_GROUPS]
     S.tslot = reinterpret_cast<uint32_t*>(bars + 2 * WS_NBUF + WS_GROUPS);
     return S;
@@ -171,16 +191,23 @@ __device__ __forceinline__ WsShared ws_carve(float* smem) {
 // barriers + tensor memory; touches no global memory (may run before pdl_wait)
 __device__ __forceinline__ void ws_init(const WsShared& S) {
     if (threadIdx.x == 0) {
-        for (int b = 0; b < WS_NBUF; ++b) { mbar_init(S.full + b, 4); mbar_init(S.empty + b, WS_CONS); }
+        for (int b = 0; b < WS_NBUF; ++b) { mbar_init(S.full + b, 4); mbar_init(S.empty + b, WS_TEAM); }
         for (int g = 0; g < WS_GROUPS; ++g) mbar_init(S.mma_bar + g, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == 0) tmem_alloc_all(S.tslot);
 }
+// the constant column block [1 0 0 0] behind h1 of every buffer row (the bias row of the layer-2 weight gradient): written
+// once; the scratch use of the buffers at the end of a sweep overwrites it, so ws_pads() is repeated after every reduction
+__device__ __forceinline__ void ws_pads(const WsShared& S) {
+    for (int i = threadIdx.x; i < WS_NBUF * WS_TILE_ROWS; i += blockDim.x) st4(S.bufs + (int64_t)i * WS_ROWF + WS_OH1 + 20, 1.f, 0.f, 0.f, 0.f);
+}
+
 // B operands from the staged parameters (canonical K-major, tf32 hi / lo): B1[n][k] = [W1; b1][k][n],
 // B2[n][k] = [W2; b2][k][n], B3[n][k] = W2[n][k].  All threads; followed by ws_operands_visible() + a CTA-wide barrier.
 template <int DIN>
 __device__ __forceinline__ void ws_build_operands(const WsShared& S) {
+    ws_pads(S);
     const float* sw = S.sw;
     for (int i = threadIdx.x; i < TC_N * 16; i += blockDim.x) {
         const int n = i / 16, k = i % 16;
@@ -209,11 +236,11 @@ __device__ __forceinline__ int ws_tile_count(int64_t n_rows, int y, int gy) {
     return (int)((ntiles > y) ? (ntiles - y + gy - 1) / gy : 0);
 }
 
-// ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  qbase = tiles pushed through the ring by earlier
-// sweeps of the same kernel (buffer index and barrier parities continue across sweeps). ----
+// ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  nbase = tiles this stream pushed through its ring in
+// earlier sweeps of the same kernel (buffer index and barrier parities continue across sweeps); advanced here. ----
 template <int NA, int DIN>
 __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows& Rw, const rcmarl_grad_job& job, int y, int gy,
-                                           int nq, uint32_t qbase, uint32_t& mph, float (&g3)[HID + 1], float& loss) {
+                                           int nq, uint32_t& nbase, uint32_t& mph, float (&g3)[HID + 1], float& loss) {
     constexpr int K1 = 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp >> 2, gwarp = warp & 3;
@@ -233,10 +260,9 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
     bool live = false;
     if (group < nq) ws_fetch<NA, DIN>(Rw, job, y, gy, group, r, xr, tgt, live);
 
-    for (int q = group; q < nq; q += WS_GROUPS) {
-        const uint32_t Q = qbase + (uint32_t)q;
-        const int b = (int)(Q % WS_NBUF);
-        const uint32_t use = Q / WS_NBUF;
+    for (int q = group; q < nq; q += WS_GROUPS, ++nbase) {
+        const int b = group * WS_RING + (int)(nbase % WS_RING);       // nbase: tiles this stream has pushed through its ring
+        const uint32_t use = nbase / WS_RING;
         float* rowp = S.bufs + ((int64_t)b * WS_TILE_ROWS + r) * WS_ROWF;
         const bool live_q = live;
         const float tgt_q = tgt;
@@ -314,8 +340,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
         }
         // ---------------- backward-data: u = delta2 . W2^T, delta1 = u * lrelu'(h1) ----------------
         {
-#pragma unroll
-            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OD2 + 4 * qq, d2[4 * qq], d2[4 * qq + 1], d2[4 * qq + 2], d2[4 * qq + 3]);
+            ws_store_halves(rowp + WS_OD2, d2);
             ws_store_operand<24>(tlane, CAH, CAL, d2);
             tmem_wait_st();
             tmem_fence_before_sync();
@@ -333,8 +358,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             float d1[HID];
 #pragma unroll
             for (int i = 0; i < HID; ++i) d1[i] = __uint_as_float(u[i]) * lrelu_grad_from_out(h1[i]);
-#pragma unroll
-            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OD1 + 4 * qq, d1[4 * qq], d1[4 * qq + 1], d1[4 * qq + 2], d1[4 * qq + 3]);
+            ws_store_halves(rowp + WS_OD1, d1);
             tmem_fence_before_sync();       // the next tile's MMAs overwrite the accumulator only after the next group barrier
         }
         __syncwarp();
@@ -342,31 +366,30 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
     }
 }
 
-// ---- consumer warp cw: tiles q = cw, cw + WS_CONS, ... of this sweep ----
-__device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, uint32_t qbase, f2 (&acc)[80]) {
+// ---- consumer warp cw (team cw / 4, member cw % 4): its team takes every second tile, the four members split the tile's
+// 43 three-row steps.  A buffer is held for a quarter of the time one warp would need, and two teams keep two buffers in
+// consumption while two are in production (ring of WS_NBUF = 5). ----
+__device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, uint32_t& nbase, f2 (&acc)[WS_ACC]) {
     const int lane = threadIdx.x & 31;
-    const bool active = lane < 5 * WS_NG;
-    const int atile = active ? lane % 5 : 0;
-    const int grp = active ? lane / 5 : 0;
-    const int acol = 8 * atile;                                       // x: 0..15, h1: 16..35 (tile 4: 4 values + [1 0 0 0])
-    const int dcol = atile < 2 ? WS_OD1 : WS_OD2;
-    const bool last_tile = atile == 4;
-    // Every consumer warp works on EVERY tile (steps cw, cw + WS_CONS, ... of its 22 six-row steps): a buffer is then held for
-    // a quarter of the time one warp would need for all of it, and with 5 buffers in the ring that residency -- production
-    // (three MMA round trips) plus consumption -- is what bounds the tile rate (first version: one warp per tile, producers
-    // spent most of their time waiting for a free buffer).
-    constexpr int FULL_STEPS = WS_TILE_ROWS / WS_NG;                  // 21 (+ rows 126, 127 as step 21)
-    for (int q = 0; q < nq; ++q) {
-        const uint32_t Q = qbase + (uint32_t)q;
-        const int b = (int)(Q % WS_NBUF);
-        const uint32_t use = Q / WS_NBUF;
+    const bool active = lane < 10 * WS_NG;
+    const int combo = active ? lane % 10 : 0;                         // (a-tile, delta half)
+    const int atile = combo % 5, half = combo / 5;
+    const int grp = active ? lane / 10 : 0;
+    const int acol = 8 * atile;                                       // x: 0..15, [h1 | 1 0 0 0]: 16..39
+    const int dcol = (atile < 2 ? WS_OD1 : WS_OD2) + WS_DHALF * half;
+    const int team = cw / WS_TEAM, member = cw % WS_TEAM;
+    constexpr int FULL_STEPS = WS_TILE_ROWS / WS_NG;                  // 42 (+ rows 126, 127 as step 42)
+    static_assert(WS_CONS / WS_TEAM == WS_GROUPS, "one consumer team per producer group");
+    for (int q = team; q < nq; q += WS_GROUPS, ++nbase) {
+        const int b = team * WS_RING + (int)(nbase % WS_RING);
+        const uint32_t use = nbase / WS_RING;
         mbar_wait_sleep<0, 100>(S.full + b, use & 1u);
         const float* buf = S.bufs + (int64_t)b * WS_TILE_ROWS * WS_ROWF;
-#pragma unroll 2
-        for (int s = cw; s < FULL_STEPS; s += WS_CONS)
-            ws_consume_row(buf + (s * WS_NG + grp) * WS_ROWF, acol, dcol, last_tile, acc);
-        if (cw == FULL_STEPS % WS_CONS && grp < WS_TILE_ROWS % WS_NG)
-            ws_consume_row(buf + (FULL_STEPS * WS_NG + grp) * WS_ROWF, acol, dcol, last_tile, acc);
+#pragma unroll 1
+        for (int s = member; s < FULL_STEPS; s += WS_TEAM)
+            ws_consume_row(buf + (s * WS_NG + grp) * WS_ROWF, acol, dcol, acc);
+        if (member == FULL_STEPS % WS_TEAM && grp < WS_TILE_ROWS % WS_NG)
+            ws_consume_row(buf + (FULL_STEPS * WS_NG + grp) * WS_ROWF, acol, dcol, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(S.empty + b);
     }
@@ -375,7 +398,7 @@ __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, ui
 // ---- end of a sweep: every thread passes (A), the roles park their sums in the (now idle) tile buffers, (B), and the CTA
 // adds them up in a fixed order; store(i, v) receives the sums for the packed parameters i = 0 .. NP-1 and the loss as NP ----
 __device__ __forceinline__ float* ws_red(const WsShared& S) { return S.bufs; }
-__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.bufs + WS_CONS * 32 * 160; }
+__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.bufs + WS_CONS * 32 * (2 * WS_ACC); }
 __device__ __forceinline__ void ws_park_producer(const WsShared& S, const float (&g3)[HID + 1], float loss) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* red3 = ws_red3(S);
@@ -387,11 +410,11 @@ __device__ __forceinline__ void ws_park_producer(const WsShared& S, const float 
         if (lane == 0) red3[warp * (HID + 2) + j] = s;
     }
 }
-__device__ __forceinline__ void ws_park_consumer(const WsShared& S, int cw, const f2 (&acc)[80]) {
+__device__ __forceinline__ void ws_park_consumer(const WsShared& S, int cw, const f2 (&acc)[WS_ACC]) {
     const int lane = threadIdx.x & 31;
-    float4* dst = reinterpret_cast<float4*>(ws_red(S) + (cw * 32 + lane) * 160);
+    float4* dst = reinterpret_cast<float4*>(ws_red(S) + (cw * 32 + lane) * (2 * WS_ACC));
 #pragma unroll
-    for (int e = 0; e < 40; ++e) {
+    for (int e = 0; e < WS_ACC / 2; ++e) {
         float4 v;
         unpack2(acc[2 * e], v.x, v.y);
         unpack2(acc[2 * e + 1], v.z, v.w);
@@ -404,13 +427,15 @@ __device__ __forceinline__ void ws_cta_sums(const WsShared& S, ST store) {
     const float* red = ws_red(S);
     const float* red3 = ws_red3(S);
     for (int qi = threadIdx.x; qi < 5 * 160; qi += WS_THREADS) {
-        const int t = qi / 160, e = qi % 160;
-        const int idx = ws_tile_param<DIN>(t, e / 20, e % 20);
+        const int t = qi / 160, e = qi % 160;                         // a-tile t, element (ii, j) = (e / 20, e % 20)
+        const int ii = e / 20, j = e % 20;
+        const int idx = ws_tile_param<DIN>(t, ii, j);
         if (idx >= 0) {
+            const int half = j / 10, slot = ii * 10 + (j % 10);       // lane combo = half * 5 + t, accumulator slot in the lane
             float s = 0.f;
             for (int c = 0; c < WS_CONS; ++c)
 #pragma unroll
-                for (int g = 0; g < WS_NG; ++g) s += red[(c * 32 + g * 5 + t) * 160 + e];
+                for (int g = 0; g < WS_NG; ++g) s += red[(c * 32 + g * 10 + half * 5 + t) * (2 * WS_ACC) + slot];
             store(idx, s);
         }
     }
@@ -448,22 +473,21 @@ __device__ __forceinline__ void ws_body(const GradParams& P, const rcmarl_grad_j
     const int nq = ws_tile_count(Rw.n_rows, y, gy);
     float* out = P.partial + (int64_t)blockIdx.x * P.stride;
     if (warp < 4 * WS_GROUPS) {
-        reg_dec<WS_REGS_PROD>();
-        uint32_t mph = 0;
+        uint32_t mph = 0, nbase = 0;
         float g3[HID + 1];
 #pragma unroll
         for (int j = 0; j <= HID; ++j) g3[j] = 0.f;
         float loss = 0.f;
-        ws_produce<NA, DIN>(S, Rw, job, y, gy, nq, 0u, mph, g3, loss);
+        ws_produce<NA, DIN>(S, Rw, job, y, gy, nq, nbase, mph, g3, loss);
         named_barrier(WS_BAR_A, WS_THREADS);                          // every tile produced and consumed
         ws_park_producer(S, g3, loss);
     } else {
-        reg_inc<WS_REGS_CONS>();
         const int cw = warp - 4 * WS_GROUPS;
-        f2 acc[80];                                                   // 8 (a) x 20 (delta), packed as pairs over the delta index
+        f2 acc[WS_ACC];                                               // 8 (a) x 10 (delta half), packed as pairs over the delta index
 #pragma unroll
-        for (int e = 0; e < 80; ++e) acc[e] = pack2(0.f, 0.f);
-        ws_consume(S, cw, nq, 0u, acc);
+        for (int e = 0; e < WS_ACC; ++e) acc[e] = pack2(0.f, 0.f);
+        uint32_t nbase = 0;
+        ws_consume(S, cw, nq, nbase, acc);
         named_barrier(WS_BAR_A, WS_THREADS);
         ws_park_consumer(S, cw, acc);
     }

@@ -13,6 +13,6 @@ echo "== mini-batch chain with v7 (persistent WS kernel), then launch chain"
 RCMARL_LIB=$P/librcmarl_v7.so timeout 200 python tools/prof_mb.py 4096 3000 3 2>&1 | tail -2
 RCMARL_LIB=$P/librcmarl_v7.so RCMARL_MB_PERSIST=0 timeout 200 python tools/prof_mb.py 4096 3000 3 2>&1 | tail -2
 echo "== ncu v7"
-RCMARL_LIB=$P/librcmarl_v7.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:grad_kernel_ws -s 2 -c 1 -o gpurun_out/prof_v7d python tools/prof_grad.py 4096000 8 3 2>&1 | tail -1
+RCMARL_LIB=$P/librcmarl_v7.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:grad_kernel_ws -s 2 -c 1 -o gpurun_out/prof_v7f python tools/prof_grad.py 4096000 8 3 2>&1 | tail -1
 echo "== bench with v7 (short)"
 RCMARL_LIB=$P/librcmarl_v7.so timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-consensus 2>/dev/null | python -c "import sys, json; d = json.loads(sys.stdin.read()); print('BENCH v7', d['value'], d['ms_per_step'], json.dumps(d['roofline']['regimes']), json.dumps(d['breakdown_ms']))"
