@@ -297,6 +297,10 @@ typedef struct {
 } rcmarl_rollout_args;
 int rcmarl_rollout(const rcmarl_rollout_args* args_host, void* stream);
 
+/* Means over the environments of the per-episode logs written by rcmarl_rollout (`est`, `ret`: [n_episodes][n_envs][n_agents])
+ * -> out [n_episodes][n_agents]: what training/train_agents.py:168-180 prints and stores per episode, for N environments. */
+int rcmarl_episode_means(const float* x, int n_episodes, int n_envs, int n_agents, float* out, void* stream);
+
 /* One transition of Grid_World.step + get_data for n_envs environments
  * (environments/grid_world.py:47-72): state int32 [n_envs][n_agents][2] updated in place. */
 int rcmarl_env_step(int32_t* state, const float* action, const int32_t* desired, int n_envs,

@@ -185,6 +185,12 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     return d;
 }
 
+// in-place form: the accumulator is tied to one register pair ("+l"), so ptxas cannot route a loop-carried accumulator through
+// a freshly loaded operand register and copy it back (17 MOVs per 40 FFMA2 in the consumer loop of grad_kernel_ws otherwise)
+__device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
     f2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));

@@ -5,7 +5,7 @@
 //
 // Why: grad_kernel (grad_kernel.cuh) runs both phases in every warp.  Its phase 1 feeds the FMA pipes from shared memory
 // (2 wavefronts per weight quad) and keeps 64 phase-2 accumulators alive meanwhile, so neither the FMA pipes (60 %) nor
-// the shared-memory pipe (74 %) saturate (profiles/r01_final_ncu.md).  The first tensor-core version (grad_kernel_tc.cuh)
+// the shared-memory pipe (74 %) saturate (profiles/r01_final_ncu.md).  The first tensor-core version (round 1, removed)
 // moved the dense products to tcgen05 but kept both phases in one thread: each 128-row tile then waits for three MMA round
 // trips in sequence and ran SLOWER (12.1 vs 10.0 ms).  Here the two halves are decoupled:
 //
@@ -23,7 +23,7 @@
 // While a producer group waits for its MMAs the other group and the consumers own the issue slots; the MMAs themselves
 // run beside the FMA pipes.
 #pragma once
-#include "grad_kernel_tc.cuh"
+#include "tc_common.cuh"
 
 namespace rcmarl {
 
@@ -121,20 +121,26 @@ __device__ __forceinline__ int ws_tile_param(int t, int ii, int j) {
     return i < HID ? off_W2(DIN) + i * HID + j : (i == HID ? off_b2(DIN) + j : -1);
 }
 
-// consumer: acc[8][10] += a (x) delta-half for one buffer row (5 LDS.128, 40 FFMA2 with a broadcast scalar operand)
-__device__ __forceinline__ void ws_consume_row(const float* __restrict__ rp, int acol, int dcol, f2 (&acc)[WS_ACC]) {
+// consumer: acc[8][10] += a (x) delta-half for one buffer row (5 LDS, 40 FFMA2 with a broadcast scalar operand); MASKED: the
+// a-values are scaled by `keep` (0 for a row beyond the tile)
+template <bool MASKED>
+__device__ __forceinline__ void ws_consume_row(const float* __restrict__ rp, int acol, int dcol, float keep, f2 (&acc)[WS_ACC]) {
     const float4 a0 = *reinterpret_cast<const float4*>(rp + acol);
     const float4 a1 = *reinterpret_cast<const float4*>(rp + acol + 4);
     const float4 d0 = *reinterpret_cast<const float4*>(rp + dcol);
     const float4 d1 = *reinterpret_cast<const float4*>(rp + dcol + 4);
     const float4 d2 = *reinterpret_cast<const float4*>(rp + dcol + 8);
     const f2 d[5] = {pack2(d0.x, d0.y), pack2(d0.z, d0.w), pack2(d1.x, d1.y), pack2(d1.z, d1.w), pack2(d2.x, d2.y)};
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if constexpr (MASKED) {
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) a[ii] *= keep;
+    }
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
         const f2 aa = pack2(a[ii], a[ii]);
 #pragma unroll
-        for (int jp = 0; jp < 5; ++jp) acc[ii * 5 + jp] = fma2(aa, d[jp], acc[ii * 5 + jp]);
+        for (int jp = 0; jp < 5; ++jp) fma2_acc(acc[ii * 5 + jp], aa, d[jp]);
     }
 }
 
@@ -236,6 +242,18 @@ __device__ __forceinline__ int ws_tile_count(int64_t n_rows, int y, int gy) {
     return (int)((ntiles > y) ? (ntiles - y + gy - 1) / gy : 0);
 }
 
+// Debug timeline (-DRCMARL_WS_TIMELINE=1, tools/ws_timeline.py): thread 0 of CTA 0 records clock64() at the stage boundaries
+// of its first tiles; read back with rcmarl_debug_timeline().  Compiled out of the shipped library.
+#ifndef RCMARL_WS_TIMELINE
+#define RCMARL_WS_TIMELINE 0
+#endif
+#if RCMARL_WS_TIMELINE
+__device__ long long g_ws_timeline[64 * 16];
+#define WS_TICK(k) do { if (tl_on && tl_tile < 64) g_ws_timeline[tl_tile * 16 + (k)] = clock64(); } while (0)
+#else
+#define WS_TICK(k) do { } while (0)
+#endif
+
 // ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  nbase = tiles this stream pushed through its ring in
 // earlier sweeps of the same kernel (buffer index and barrier parities continue across sweeps); advanced here. ----
 template <int NA, int DIN>
@@ -245,59 +263,82 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp >> 2, gwarp = warp & 3;
     const int r = gwarp * 32 + lane;                                 // row of the tile = TMEM lane
-    const uint32_t tmem = *S.tslot + (uint32_t)(group * 128);        // this group's column window
+    const uint32_t tmem = *S.tslot + (uint32_t)(group * 256);        // this group's column window
     const uint32_t tlane = tmem + ((uint32_t)(gwarp * 32) << 16);
-    constexpr int CAH = 0, CAL = 24, CD = 48;                        // A hi / lo (up to 24 columns each), accumulator (32)
+    // columns: layer-1 operand hi / lo | layer-2 and backward operand hi / lo | layer-1 accumulator | layer-2 / backward acc.
+    constexpr int CA1H = 0, CA1L = 16, CA2H = 32, CA2L = 56, CD1 = 80, CD2 = 112;
     const uint32_t idesc = umma_idesc_tf32(128, TC_N);
     const bool issuer = (gwarp == 0) && (lane == 0);
     uint64_t* mbar = S.mma_bar + group;
     const SmemW W{S.sw};
+#if RCMARL_WS_TIMELINE
+    const bool tl_on = blockIdx.x == 0 && threadIdx.x == 0;
+    int tl_tile = -1;
+#endif
+    if (group >= nq) return;
 
-    // inputs of a tile: the row's features and target; loaded one tile ahead (the registers of x are free once the
-    // layer-1 operand is in TMEM, so the next tile's loads fly during the three MMA round trips of this one)
+    // Schedule of one stream (the tiles q = group, group + 2, ... of this CTA), two MMA round trips per tile instead of three:
+    //   prologue   x(q0) -> TMEM, L1(q0)                                   -> h1(q0)
+    //   per tile   h1 -> TMEM, L2(q)                                         -> h2, e, delta2
+    //              delta2 -> TMEM  and  x(next) -> TMEM,  L3(q) + L1(next)   -> delta1(q) (tile complete), h1(next)
+    // The next tile's first layer rides on the current tile's backward product (independent operands, one commit, one wait);
+    // the inputs of the tile after that are fetched while those MMAs run.
     float xr[DIN];
     float tgt = 0.f;
     bool live = false;
-    if (group < nq) ws_fetch<NA, DIN>(Rw, job, y, gy, group, r, xr, tgt, live);
+    float h1[HID];
+    ws_fetch<NA, DIN>(Rw, job, y, gy, group, r, xr, tgt, live);
+    {   // ---------------- prologue: layer 1 of the stream's first tile ----------------
+        float x[K1];
+#pragma unroll
+        for (int k = 0; k < DIN; ++k) x[k] = xr[k];
+#pragma unroll
+        for (int k = DIN; k < K1; ++k) x[k] = (k == DIN) ? 1.f : 0.f;
+        ws_store_operand<K1>(tlane, CA1H, CA1L, x);
+        tmem_wait_st();
+        tmem_fence_before_sync();
+        named_barrier(1 + group, 128);
+        if (issuer) {
+            tmem_fence_after_sync();
+            tc_issue<K1>(tmem + CD1, tmem + CA1H, tmem + CA1L, S.b1h, S.b1l, idesc);
+            umma_commit(mbar);
+        }
+        mbar_wait_sleep<120, 40>(mbar, mph);
+        mph ^= 1u;
+        tmem_fence_after_sync();
+        uint32_t z[24];
+        tmem_load<24>(tlane + CD1, z);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            const float zz = __uint_as_float(z[j]);
+            h1[j] = fmaxf(zz, SLOPE * zz);
+        }
+    }
 
     for (int q = group; q < nq; q += WS_GROUPS, ++nbase) {
+#if RCMARL_WS_TIMELINE
+        ++tl_tile;
+#endif
+        WS_TICK(0);
         const int b = group * WS_RING + (int)(nbase % WS_RING);       // nbase: tiles this stream has pushed through its ring
-        const uint32_t use = nbase / WS_RING;
         float* rowp = S.bufs + ((int64_t)b * WS_TILE_ROWS + r) * WS_ROWF;
-        const bool live_q = live;
-        const float tgt_q = tgt;
-        float h1[HID];
-        // ---------------- layer 1 ----------------
-        {
-            float x[K1];
-#pragma unroll
-            for (int k = 0; k < DIN; ++k) x[k] = xr[k];
-#pragma unroll
-            for (int k = DIN; k < K1; ++k) x[k] = (k == DIN) ? 1.f : 0.f;
-            mbar_wait_sleep<0, 200>(S.empty + b, (use & 1u) ^ 1u);   // the consumer is done with the buffer's previous use
-#pragma unroll
-            for (int qq = 0; qq < K1 / 4; ++qq) st4(rowp + WS_OX + 4 * qq, x[4 * qq], x[4 * qq + 1], x[4 * qq + 2], x[4 * qq + 3]);
-            ws_store_operand<K1>(tlane, CAH, CAL, x);
-            tmem_wait_st();
-            tmem_fence_before_sync();
-            named_barrier(1 + group, 128);
-            if (issuer) {
-                tmem_fence_after_sync();
-                tc_issue<K1>(tmem + CD, tmem + CAH, tmem + CAL, S.b1h, S.b1l, idesc, mbar);
-            }
-            if (q + WS_GROUPS < nq) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);   // next tile's inputs
-            mbar_wait_sleep<120, 40>(mbar, mph);
-            mph ^= 1u;
-            tmem_fence_after_sync();
-            uint32_t z[24];
-            tmem_load<24>(tlane + CD, z);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < HID; ++j) {
-                const float zz = __uint_as_float(z[j]);
-                h1[j] = fmaxf(zz, SLOPE * zz);
-            }
+        const bool has_next = q + WS_GROUPS < nq;
+        // this tile's features are still in xr (their layer-1 product is done): claim the buffer, file them, then start the
+        // next tile's loads (they have the two MMA round trips of this tile to arrive)
+        mbar_wait_sleep<0, 200>(S.empty + b, ((nbase / WS_RING) & 1u) ^ 1u);   // the consumers are done with the buffer's previous use
+        st4(rowp + WS_OX, xr[0], xr[1], xr[2], xr[3]);
+        st4(rowp + WS_OX + 4, xr[4], xr[5], xr[6], xr[7]);
+        if constexpr (DIN == 15) {
+            st4(rowp + WS_OX + 8, xr[8], xr[9], xr[10], xr[11]);
+            st4(rowp + WS_OX + 12, xr[12], xr[13], xr[14], 1.f);
+        } else {
+            st4(rowp + WS_OX + 8, xr[8], xr[9], 1.f, 0.f);
+            st4(rowp + WS_OX + 12, 0.f, 0.f, 0.f, 0.f);
         }
+        const float tgt_q = tgt;
+        const bool live_q = live;
+        if (has_next) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);
         // ---------------- layer 2, output layer, delta2 ----------------
         float d2[24];
         {
@@ -307,20 +348,25 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             a2[20] = 1.f; a2[21] = 0.f; a2[22] = 0.f; a2[23] = 0.f;
 #pragma unroll
             for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
-            ws_store_operand<24>(tlane, CAH, CAL, a2);
+            ws_store_operand<24>(tlane, CA2H, CA2L, a2);
             tmem_wait_st();
             tmem_fence_before_sync();
+            WS_TICK(1);
             named_barrier(1 + group, 128);
+            WS_TICK(2);
             if (issuer) {
                 tmem_fence_after_sync();
-                tc_issue<24>(tmem + CD, tmem + CAH, tmem + CAL, S.b2h, S.b2l, idesc, mbar);
+                tc_issue<24>(tmem + CD2, tmem + CA2H, tmem + CA2L, S.b2h, S.b2l, idesc);
+                umma_commit(mbar);
             }
             mbar_wait_sleep<120, 40>(mbar, mph);
+            WS_TICK(3);
             mph ^= 1u;
             tmem_fence_after_sync();
             uint32_t z[24];
-            tmem_load<24>(tlane + CD, z);
+            tmem_load<24>(tlane + CD2, z);
             tmem_wait_ld();
+            WS_TICK(4);
             float h2[HID];
 #pragma unroll
             for (int j = 0; j < HID; ++j) {
@@ -338,31 +384,56 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             g3[HID] += e;
             d2[20] = 0.f; d2[21] = 0.f; d2[22] = 0.f; d2[23] = 0.f;
         }
-        // ---------------- backward-data: u = delta2 . W2^T, delta1 = u * lrelu'(h1) ----------------
+        // ---------------- backward-data of this tile + layer 1 of the stream's next tile ----------------
         {
             ws_store_halves(rowp + WS_OD2, d2);
-            ws_store_operand<24>(tlane, CAH, CAL, d2);
+            ws_store_operand<24>(tlane, CA2H, CA2L, d2);
+            if (has_next) {                                           // xr holds the next tile's features by now
+                float x[K1];
+#pragma unroll
+                for (int k = 0; k < DIN; ++k) x[k] = xr[k];
+#pragma unroll
+                for (int k = DIN; k < K1; ++k) x[k] = (k == DIN) ? 1.f : 0.f;
+                ws_store_operand<K1>(tlane, CA1H, CA1L, x);
+            }
             tmem_wait_st();
             tmem_fence_before_sync();
+            WS_TICK(5);
             named_barrier(1 + group, 128);
+            WS_TICK(6);
             if (issuer) {
                 tmem_fence_after_sync();
-                tc_issue<24>(tmem + CD, tmem + CAH, tmem + CAL, S.b3h, S.b3l, idesc, mbar);
+                tc_issue<24>(tmem + CD2, tmem + CA2H, tmem + CA2L, S.b3h, S.b3l, idesc);
+                if (has_next) tc_issue<K1>(tmem + CD1, tmem + CA1H, tmem + CA1L, S.b1h, S.b1l, idesc);
+                umma_commit(mbar);
             }
             mbar_wait_sleep<120, 40>(mbar, mph);
+            WS_TICK(7);
             mph ^= 1u;
             tmem_fence_after_sync();
             uint32_t u[24];
-            tmem_load<24>(tlane + CD, u);
+            tmem_load<24>(tlane + CD2, u);
             tmem_wait_ld();
             float d1[HID];
 #pragma unroll
             for (int i = 0; i < HID; ++i) d1[i] = __uint_as_float(u[i]) * lrelu_grad_from_out(h1[i]);
             ws_store_halves(rowp + WS_OD1, d1);
-            tmem_fence_before_sync();       // the next tile's MMAs overwrite the accumulator only after the next group barrier
+            __syncwarp();
+            if (lane == 0) mbar_arrive(S.full + b);                   // release: this warp's 32 rows of the buffer are complete
+            WS_TICK(8);
+            if (has_next) {
+                uint32_t z[24];
+                tmem_load<24>(tlane + CD1, z);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < HID; ++j) {
+                    const float zz = __uint_as_float(z[j]);
+                    h1[j] = fmaxf(zz, SLOPE * zz);
+                }
+            }
+            tmem_fence_before_sync();       // the next MMAs overwrite the accumulators only after the next group barrier
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(S.full + b);                       // release: this warp's 32 rows of the buffer are complete
+        WS_TICK(9);
     }
 }
 
@@ -385,11 +456,17 @@ __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, ui
         const uint32_t use = nbase / WS_RING;
         mbar_wait_sleep<0, 100>(S.full + b, use & 1u);
         const float* buf = S.bufs + (int64_t)b * WS_TILE_ROWS * WS_ROWF;
-#pragma unroll 1
-        for (int s = member; s < FULL_STEPS; s += WS_TEAM)
-            ws_consume_row(buf + (s * WS_NG + grp) * WS_ROWF, acol, dcol, acc);
-        if (member == FULL_STEPS % WS_TEAM && grp < WS_TILE_ROWS % WS_NG)
-            ws_consume_row(buf + (FULL_STEPS * WS_NG + grp) * WS_ROWF, acol, dcol, acc);
+        // member m takes steps m, m + 4, ... of the 43 three-row steps: ten for everybody plus an eleventh whose rows may lie
+        // beyond the tile (members 2 and 3: rows 128+), handled branch-free by clamping the row and zeroing its a-values.  All
+        // eleven steps are straight-line code: as a loop (or behind a branch) ptxas copied 17 accumulators around per step.
+        const float* rp = buf + (member * WS_NG + grp) * WS_ROWF;
+#pragma unroll
+        for (int k = 0; k < FULL_STEPS / WS_TEAM; ++k) ws_consume_row<false>(rp + k * (WS_TEAM * WS_NG * WS_ROWF), acol, dcol, 1.f, acc);
+        {
+            const int rowi = ((FULL_STEPS / WS_TEAM) * WS_TEAM + member) * WS_NG + grp;
+            const int rowc = rowi < WS_TILE_ROWS ? rowi : WS_TILE_ROWS - 1;
+            ws_consume_row<true>(buf + rowc * WS_ROWF, acol, dcol, rowi < WS_TILE_ROWS ? 1.f : 0.f, acc);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(S.empty + b);
     }

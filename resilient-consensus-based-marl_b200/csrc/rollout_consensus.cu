@@ -413,6 +413,24 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ rc
     for (int i = 0; i < NA; ++i) retp[i] = ret[i];
 }
 
+// Per-episode means over the environments of the logged quantities (train_agents.py:168-180 prints per-episode values; with
+// N environments they become means): out[ep][agent] = mean_e x[ep][e][agent], fixed-order tree.
+__global__ void __launch_bounds__(256) episode_mean_kernel(const float* __restrict__ x, int n_envs, int n_agents,
+                                                           float* __restrict__ out) {
+    __shared__ float sh[256];
+    const int ep = blockIdx.x, ag = blockIdx.y;
+    const float* p = x + (int64_t)ep * n_envs * n_agents + ag;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < n_envs; e += 256) s += p[(int64_t)e * n_agents];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[ep * n_agents + ag] = sh[0] / (float)n_envs;
+}
+
 template <int NA>
 static int launch_rollout(const rcmarl_rollout_args& A, cudaStream_t st) {
     constexpr int DIN = 2 * NA;
@@ -484,6 +502,13 @@ int rcmarl_rollout(const rcmarl_rollout_args* a, void* stream) {
     if (a->n_agents == 5) return launch_rollout<5>(*a, st);
     if (a->n_agents == 16) return launch_rollout<16>(*a, st);
     return RCMARL_ERR_ARG;
+}
+
+int rcmarl_episode_means(const float* x, int n_episodes, int n_envs, int n_agents, float* out, void* stream) {
+    if (!x || !out || n_episodes < 1 || n_envs < 1 || n_agents < 1 || n_agents > 65535) return RCMARL_ERR_ARG;
+    episode_mean_kernel<<<dim3((unsigned)n_episodes, (unsigned)n_agents), 256, 0, (cudaStream_t)stream>>>(x, n_envs, n_agents, out);
+    RC_CUDA(cudaGetLastError());
+    return RCMARL_OK;
 }
 
 int rcmarl_env_step(int32_t* state, const float* action, const int32_t* desired, int n_envs, int n_agents, int nrow,

@@ -15,27 +15,9 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "grad_kernel.cuh"
-// RCMARL_GRAD_V4=1 (make variant_v5): the experimental TMEM-parked exact-fit-tile kernel replaces grad_kernel
-#ifndef RCMARL_GRAD_V4
-#define RCMARL_GRAD_V4 0
-#endif
-#if RCMARL_GRAD_V4
-#include "grad_kernel_v4.cuh"
-#define RC_GRAD_KERNEL grad_kernel_v4
-#define RC_GRAD_WARPS grad4_warps
-#define RC_GRAD_SMEM grad4_smem_floats
-#else
 #define RC_GRAD_KERNEL grad_kernel
 #define RC_GRAD_WARPS grad_warps
 #define RC_GRAD_SMEM grad_smem_floats
-#endif
-// RCMARL_GRAD_TC=1 (make variant_v6): mean-squared-error jobs at n_agents = 5 run on the experimental tensor-core hybrid
-#ifndef RCMARL_GRAD_TC
-#define RCMARL_GRAD_TC 0
-#endif
-#if RCMARL_GRAD_TC
-#include "grad_kernel_tc.cuh"
-#endif
 // RCMARL_GRAD_WS (default 1): mean-squared-error jobs at n_agents = 5 run on the warp-specialised tensor-core kernel
 // (grad_kernel_ws.cuh); -DRCMARL_GRAD_WS=0 (make variant_ffma) keeps them on the FFMA2 kernel of round 1 (grad_kernel.cuh)
 #ifndef RCMARL_GRAD_WS
@@ -514,18 +496,6 @@ static int launch_grad(GradParams& P, int loss_mode, int n_ctas, cudaStream_t st
         cfg.blockDim = dim3(WS_THREADS);
         cfg.dynamicSmemBytes = smem_ws;
         RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel_ws, P));
-#elif RCMARL_GRAD_TC
-    } else if (NA == 5) {
-        constexpr size_t smem_tc = sizeof(float) * (grad_tc_smem_floats<15>() > grad_tc_smem_floats<10>()
-                                                        ? grad_tc_smem_floats<15>() : grad_tc_smem_floats<10>());
-        static bool attr_tc = false;
-        if (!attr_tc) {
-            if (set_smem(grad_kernel_tc, smem_tc)) return RCMARL_ERR_CUDA;
-            attr_tc = true;
-        }
-        cfg.blockDim = dim3(32 * TC_WARPS);
-        cfg.dynamicSmemBytes = smem_tc;
-        RC_CUDA(cudaLaunchKernelEx(&cfg, grad_kernel_tc, P));
 #endif
     } else {
         if (!attr_mse) {
@@ -545,8 +515,6 @@ template <int NA>
 static int grad_chunks_per_cta(int loss_mode) {
 #if RCMARL_GRAD_WS
     if (NA == 5 && loss_mode == RCMARL_LOSS_MSE) return 2;      // one 128-row tile (= two 64-row chunks) at a time
-#elif RCMARL_GRAD_TC
-    if (NA == 5 && loss_mode == RCMARL_LOSS_MSE) return 4;      // two 128-row tiles (= four 64-row chunks) per CTA and round
 #endif
     return loss_mode == RCMARL_LOSS_CE ? RC_GRAD_WARPS<NA, RCMARL_LOSS_CE>() : RC_GRAD_WARPS<NA, RCMARL_LOSS_MSE>();
 }
@@ -953,7 +921,7 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
 #if RCMARL_GRAD_WS
     {   // 2 .. MB_IL_MAX chains of a 5-agent team: every CTA serves every chain in turn (RCMARL_MB_INTERLEAVE=0: exclusive shares)
         static int il = -1;
-        if (il < 0) { const char* e = getenv("RCMARL_MB_INTERLEAVE"); il = e ? (e[0] != '0') : 1; }
+        if (il < 0) { const char* e = getenv("RCMARL_MB_INTERLEAVE"); il = e ? (e[0] != '0') : 0; }
         interleaved = il && NA == 5 && n_jobs >= 2 && n_jobs <= MB_IL_MAX;
     }
 #endif
@@ -994,6 +962,15 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
 #endif
     return NA == 5 ? launch_mb_persist<5>(P, n_ctas, st) : launch_mb_persist<16>(P, n_ctas, st);
 }
+
+#if RCMARL_GRAD_WS && RCMARL_WS_TIMELINE
+/* debug builds only (csrc/Makefile variant_tl): stage timestamps of the first producer thread, [64 tiles][16 ticks] */
+int rcmarl_debug_timeline(long long* out_host, int n) {
+    if (!out_host || n < 1 || n > 64 * 16) return RCMARL_ERR_ARG;
+    RC_CUDA(cudaMemcpyFromSymbol(out_host, g_ws_timeline, sizeof(long long) * n));
+    return RCMARL_OK;
+}
+#endif
 
 int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs, void* ws, int64_t ws_bytes,
                 void* stream) {

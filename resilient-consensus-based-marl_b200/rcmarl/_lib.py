@@ -105,6 +105,7 @@ SYMBOLS = [
     ("rcmarl_comm_error", C.c_int, [C.c_void_p]),
     ("rcmarl_comm_destroy", C.c_int, [C.c_void_p]),
     ("rcmarl_rollout", C.c_int, [C.POINTER(RolloutArgs), c_fp]),
+    ("rcmarl_episode_means", C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     ("rcmarl_env_step", C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
 ]
 

@@ -276,6 +276,15 @@ def rollout(actor_w, critic_w, desired, sa, ns, r, time_begin, est, ret, *, n_en
     L.check(L.lib().rcmarl_rollout(C.byref(A), _stream()), "rcmarl_rollout")
 
 
+def episode_means(x, out=None):
+    """x: [n_episodes, n_envs, n_agents] float32 CUDA -> [n_episodes, n_agents] means over the environments."""
+    n_ep, n_envs, n_agents = x.shape
+    if out is None:
+        out = torch.empty(n_ep, n_agents, dtype=torch.float32, device=x.device)
+    L.check(L.lib().rcmarl_episode_means(x.data_ptr(), n_ep, n_envs, n_agents, out.data_ptr(), _stream()), "rcmarl_episode_means")
+    return out
+
+
 def env_step(state, action, desired, nrow, reward=None):
     n_envs, n_agents = state.shape[0], state.shape[1]
     if reward is None:

@@ -204,7 +204,10 @@ class Trainer:
         self.launches += 1
         self.t_filled += n_ep * Lq
         self.episodes_done += n_ep
-        stats = torch.stack([est.mean(dim=1), ret.mean(dim=1)])          # logging only
+        stats = torch.empty(2, n_ep, self.NA, dtype=torch.float32, device=self.dev)
+        ops.episode_means(est, stats[0])                                   # logging only (train_agents.py:168-180)
+        ops.episode_means(ret, stats[1])
+        self.launches += 2
         if self.world > 1:
             dist_util.allreduce_sums(stats, self.world, self.group)     # logging only (NCCL)
             stats /= self.world
@@ -409,8 +412,10 @@ class Trainer:
             n = self.PT if kind == L.IN_SA else self.PC
             sums = self.sums_mb[c][:n + 1]
             gj.append(ops.grad_job(w, tgt, sums, kind, target_stride=st, time_idx=perms))
-            aj.append(ops.sgd_job(w, w, sums, n, 0.0, loss_out=loss, loss_coef=1.0 / (T * N * self.world), loss_accumulate=1))
-            if loss is not None:
+            persistent = self.mb_cells is not None and (self.world == 1 or self.comm is not None)
+            aj.append(ops.sgd_job(w, w, sums, n, 0.0, loss_out=loss, loss_coef=1.0 / (T * N * self.world),
+                                  loss_accumulate=0 if persistent else 1))     # the persistent kernel writes the epoch-0 loss once
+            if loss is not None and not persistent:
                 loss.zero_()
         gj, aj = (L.GradJob * len(gj))(*gj), (L.SgdJob * len(aj))(*aj)
         rows = self._rows(0, 0, perms)

@@ -9,11 +9,9 @@ echo "== mini-batch chain: interleaved, exclusive shares, launch chain"
 timeout 200 python tools/prof_mb.py 4096 3000 3 2>&1 | tail -2
 RCMARL_MB_INTERLEAVE=0 timeout 200 python tools/prof_mb.py 4096 3000 3 2>&1 | tail -2
 RCMARL_MB_PERSIST=0 timeout 200 python tools/prof_mb.py 4096 3000 3 2>&1 | tail -2
-echo "== v9 (buffer rows of 92 floats, integer tf32 split): grad timing default / v9, tests, mini-batch"
+echo "== grad timing: default (tcgen05 WS) and the FFMA2 build"
 timeout 200 python tools/ab_grad.py time 2>&1 | grep TIMING
-RCMARL_LIB=$P/librcmarl_v9.so timeout 200 python tools/ab_grad.py time 2>&1 | grep TIMING
-RCMARL_LIB=$P/librcmarl_v9.so timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_trainer_gpu.py tests/test_benchshape_parity_gpu.py -m gpu -q 2>&1 | tail -4
-RCMARL_LIB=$P/librcmarl_v9.so timeout 200 python tools/prof_mb.py 4096 3000 3 2>&1 | tail -2
+RCMARL_LIB=$P/librcmarl_ffma.so timeout 200 python tools/ab_grad.py time 2>&1 | grep TIMING
 echo "== bench (short)"
 timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-consensus > gpurun_out/bench_call9.json 2> gpurun_out/bench_call9.err
 python - <<'PY'
