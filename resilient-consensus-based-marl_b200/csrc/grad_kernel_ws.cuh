@@ -9,17 +9,19 @@
 // moved the dense products to tcgen05 but kept both phases in one thread: each 128-row tile then waits for three MMA round
 // trips in sequence and ran SLOWER (12.1 vs 10.0 ms).  Here the two halves are decoupled:
 //
-//   producer groups (2 x 4 warps, thread = buffer row = TMEM lane, ~100 registers)
+//   producer groups (2 x 4 warps, thread = buffer row = TMEM lane, 128 registers)
 //       z1 = [x | 1] . [W1; b1]   ->  h1 = lrelu(z1)          tcgen05.mma, A operand written to TMEM by the row's thread as
 //       z2 = [h1 | 1] . [W2; b2]  ->  h2, out, e, delta2       tf32 hi / lo halves, B = split weights in shared memory,
 //       u  = delta2 . W2^T        ->  delta1 = u * lrelu'(h1)  accumulator read back with tcgen05.ld
-//     and write the row's [x | h1 | delta1 | delta2] into a shared-memory tile buffer (ring of WS_NBUF 128-row buffers);
-//     the output-layer gradient (21 values) and the loss are accumulated per thread.
-//   consumer warps (4, one per scheduler, 240 registers)
-//       sum over the buffer's rows of the outer products [x | 1] (x) delta1 and [h1 | 1] (x) delta2 as 8 x 20 register
-//       tiles (5 tiles x 6 row groups per warp; 7 LDS.128 per 80 FFMA2), accumulated across ALL tiles of the CTA.
-//   Buffers are handed over with full / empty mbarriers; tile q goes to producer group q % 2, buffer q % WS_NBUF and
-//   consumer team q % 2 (static, so every sum keeps a fixed order: results are bitwise reproducible).
+//     and write the row's [x | h1 | delta1 | delta2] into a shared-memory tile buffer (two 128-row buffers per group); the
+//     output-layer gradient (21 values) and the loss are accumulated per thread.  A tile costs two MMA round trips, not
+//     three: the next tile's first layer is issued together with this tile's backward product (ws_produce).
+//   consumer warps (2 teams x 4 warps, two per scheduler, 128 registers)
+//       sum over the buffer's rows of the outer products [x | 1] (x) delta1 and [h1 | 1] (x) delta2 as 8 x 10 register
+//       tiles (5 a-tiles x 2 delta halves x 3 row groups = 30 lanes per warp; 5 LDS.128 per 40 FFMA2), accumulated across
+//       ALL tiles of the CTA.
+//   Buffers are handed over with full / empty mbarriers; tile q goes to producer group q % 2, that group's ring buffer
+//   (q / 2) % 2 and consumer team q % 2 (static, so every sum keeps a fixed order: results are bitwise reproducible).
 // While a producer group waits for its MMAs the other group and the consumers own the issue slots; the MMAs themselves
 // run beside the FMA pipes.
 #pragma once
@@ -32,8 +34,8 @@ namespace rcmarl {
 #endif
 constexpr int WS_GROUPS = RCMARL_WS_GROUPS;                   // producer groups of 4 warps (2 or 3)
 constexpr int WS_CONS = 8;                                    // consumer warps (two per scheduler), in two teams of four
-constexpr int WS_WARPS = 4 * WS_GROUPS + WS_CONS;             // 12
-constexpr int WS_THREADS = 32 * WS_WARPS;                     // 384
+constexpr int WS_WARPS = 4 * WS_GROUPS + WS_CONS;             // 16
+constexpr int WS_THREADS = 32 * WS_WARPS;                     // 512
 constexpr int WS_RING = 2;                                    // tile buffers per stream (producer group g <-> consumer team g)
 constexpr int WS_NBUF = WS_RING * WS_GROUPS;                  // 4: each stream owns its own ring -- the uses of a buffer are then
                                                               // strictly ordered by ONE producer / consumer pair, which the
@@ -52,15 +54,38 @@ constexpr int WS_ACC = 40;                                    // packed accumula
 // 16 warps x 32 lanes x 128 registers = the whole register file: no setmaxnreg needed (the first versions ran 4 consumer
 // warps with 8 x 20 tiles at 240 registers; one FFMA2 stream per scheduler issued only ~30 % of the cycles, and the consumers
 // were the bottleneck -- two narrower consumer warps per scheduler cover each other's latencies)
-constexpr int WS_REGS_PROD = 128, WS_REGS_CONS = 128;
+// back-off of a producer group waiting for its MMAs: first sleep after the layer-2 batch (9 MMAs) / after the merged backward +
+// next-layer-1 batch (15 MMAs), then the poll interval, in ns (a sweep of 0 .. 450 ns changed nothing, profiles/r02_kernel_experiments.md)
+#ifndef RCMARL_WS_SLEEP2
+#define RCMARL_WS_SLEEP2 120
+#endif
+#ifndef RCMARL_WS_SLEEP3
+#define RCMARL_WS_SLEEP3 120
+#endif
+#ifndef RCMARL_WS_POLL
+#define RCMARL_WS_POLL 40
+#endif
+// Which producer bookkeeping runs in the shadow of the tile's MMA batches instead of ahead of them (bit 0: buffer claim + x / h1
+// filing and bit 1: the next tile's loads, behind the layer-2 issue; bit 2: delta2 filing behind the backward issue).  Measured
+// per regime (profiles/r02_kernel_experiments.md): the long sweeps of rcmarl_grad are fastest with everything ahead (7.91 vs
+// 8.31 ms), the 10-tile sweeps of a mini-batch step with everything deferred (47.4 vs 50.3 us per step).
+#ifndef RCMARL_WS_SHADOW_SWEEP
+#define RCMARL_WS_SHADOW_SWEEP 0
+#endif
+#ifndef RCMARL_WS_SHADOW_STEP
+#define RCMARL_WS_SHADOW_STEP 7
+#endif
+constexpr int WS_SHADOW_SWEEP = RCMARL_WS_SHADOW_SWEEP, WS_SHADOW_STEP = RCMARL_WS_SHADOW_STEP;
+#ifndef RCMARL_WS_POLL_EMPTY                                   // producers waiting for a free buffer / consumers for a full one
+#define RCMARL_WS_POLL_EMPTY 200
+#endif
+#ifndef RCMARL_WS_POLL_FULL
+#define RCMARL_WS_POLL_FULL 100
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 // mbarrier wait with back-off.  try_wait returns after a few tens of nanoseconds whether or not the phase completed, so a
 // plain poll loop is ~6 instructions per iteration per waiting warp; in the first version a third of all issued instructions
 // were wait loops, and they competed for issue slots with the consumer warp of the same scheduler (the FMA pipes were 45 %
@@ -256,9 +281,10 @@ __device__ long long g_ws_timeline[64 * 16];
 
 // ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  nbase = tiles this stream pushed through its ring in
 // earlier sweeps of the same kernel (buffer index and barrier parities continue across sweeps); advanced here. ----
-template <int NA, int DIN>
+template <int NA, int DIN, int SHADOW>
 __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows& Rw, const rcmarl_grad_job& job, int y, int gy,
                                            int nq, uint32_t& nbase, uint32_t& mph, float (&g3)[HID + 1], float& loss) {
+    static_assert((SHADOW & 3) != 1, "the next tile's loads overwrite the features the deferred filing still needs");
     constexpr int K1 = 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp >> 2, gwarp = warp & 3;
@@ -303,7 +329,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             tc_issue<K1>(tmem + CD1, tmem + CA1H, tmem + CA1L, S.b1h, S.b1l, idesc);
             umma_commit(mbar);
         }
-        mbar_wait_sleep<120, 40>(mbar, mph);
+        mbar_wait_sleep<RCMARL_WS_SLEEP2, RCMARL_WS_POLL>(mbar, mph);
         mph ^= 1u;
         tmem_fence_after_sync();
         uint32_t z[24];
@@ -324,21 +350,25 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
         const int b = group * WS_RING + (int)(nbase % WS_RING);       // nbase: tiles this stream has pushed through its ring
         float* rowp = S.bufs + ((int64_t)b * WS_TILE_ROWS + r) * WS_ROWF;
         const bool has_next = q + WS_GROUPS < nq;
-        // this tile's features are still in xr (their layer-1 product is done): claim the buffer, file them, then start the
-        // next tile's loads (they have the two MMA round trips of this tile to arrive)
-        mbar_wait_sleep<0, 200>(S.empty + b, ((nbase / WS_RING) & 1u) ^ 1u);   // the consumers are done with the buffer's previous use
-        st4(rowp + WS_OX, xr[0], xr[1], xr[2], xr[3]);
-        st4(rowp + WS_OX + 4, xr[4], xr[5], xr[6], xr[7]);
-        if constexpr (DIN == 15) {
-            st4(rowp + WS_OX + 8, xr[8], xr[9], xr[10], xr[11]);
-            st4(rowp + WS_OX + 12, xr[12], xr[13], xr[14], 1.f);
-        } else {
-            st4(rowp + WS_OX + 8, xr[8], xr[9], 1.f, 0.f);
-            st4(rowp + WS_OX + 12, 0.f, 0.f, 0.f, 0.f);
+        if constexpr ((SHADOW & 1) == 0) {
+            mbar_wait_sleep<0, RCMARL_WS_POLL_EMPTY>(S.empty + b, ((nbase / WS_RING) & 1u) ^ 1u);
+            st4(rowp + WS_OX, xr[0], xr[1], xr[2], xr[3]);
+            st4(rowp + WS_OX + 4, xr[4], xr[5], xr[6], xr[7]);
+            if constexpr (DIN == 15) {
+                st4(rowp + WS_OX + 8, xr[8], xr[9], xr[10], xr[11]);
+                st4(rowp + WS_OX + 12, xr[12], xr[13], xr[14], 1.f);
+            } else {
+                st4(rowp + WS_OX + 8, xr[8], xr[9], 1.f, 0.f);
+                st4(rowp + WS_OX + 12, 0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
         }
         const float tgt_q = tgt;
         const bool live_q = live;
-        if (has_next) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);
+        if constexpr ((SHADOW & 2) == 0) {
+            if (has_next) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);
+        }
         // ---------------- layer 2, output layer, delta2 ----------------
         float d2[24];
         {
@@ -346,8 +376,6 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
 #pragma unroll
             for (int j = 0; j < HID; ++j) a2[j] = h1[j];
             a2[20] = 1.f; a2[21] = 0.f; a2[22] = 0.f; a2[23] = 0.f;
-#pragma unroll
-            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
             ws_store_operand<24>(tlane, CA2H, CA2L, a2);
             tmem_wait_st();
             tmem_fence_before_sync();
@@ -359,7 +387,27 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
                 tc_issue<24>(tmem + CD2, tmem + CA2H, tmem + CA2L, S.b2h, S.b2l, idesc);
                 umma_commit(mbar);
             }
-            mbar_wait_sleep<120, 40>(mbar, mph);
+            // In the shadow of those MMAs: claim the tile buffer (the consumers are done with its previous use), file this tile's
+            // features (still in xr: their layer-1 product is done) and h1, then start the next tile's loads -- they have the
+            // rest of this round trip and the output-layer arithmetic to arrive.  None of it is on the path to the next issue.
+            if constexpr ((SHADOW & 1) != 0) {
+            mbar_wait_sleep<0, RCMARL_WS_POLL_EMPTY>(S.empty + b, ((nbase / WS_RING) & 1u) ^ 1u);
+            st4(rowp + WS_OX, xr[0], xr[1], xr[2], xr[3]);
+            st4(rowp + WS_OX + 4, xr[4], xr[5], xr[6], xr[7]);
+            if constexpr (DIN == 15) {
+                st4(rowp + WS_OX + 8, xr[8], xr[9], xr[10], xr[11]);
+                st4(rowp + WS_OX + 12, xr[12], xr[13], xr[14], 1.f);
+            } else {
+                st4(rowp + WS_OX + 8, xr[8], xr[9], 1.f, 0.f);
+                st4(rowp + WS_OX + 12, 0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
+            }
+            if constexpr ((SHADOW & 2) != 0) {
+                if (has_next) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);
+            }
+            mbar_wait_sleep<RCMARL_WS_SLEEP2, RCMARL_WS_POLL>(mbar, mph);
             WS_TICK(3);
             mph ^= 1u;
             tmem_fence_after_sync();
@@ -386,7 +434,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
         }
         // ---------------- backward-data of this tile + layer 1 of the stream's next tile ----------------
         {
-            ws_store_halves(rowp + WS_OD2, d2);
+            if constexpr ((SHADOW & 4) == 0) ws_store_halves(rowp + WS_OD2, d2);
             ws_store_operand<24>(tlane, CA2H, CA2L, d2);
             if (has_next) {                                           // xr holds the next tile's features by now
                 float x[K1];
@@ -407,7 +455,8 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
                 if (has_next) tc_issue<K1>(tmem + CD1, tmem + CA1H, tmem + CA1L, S.b1h, S.b1l, idesc);
                 umma_commit(mbar);
             }
-            mbar_wait_sleep<120, 40>(mbar, mph);
+            if constexpr ((SHADOW & 4) != 0) ws_store_halves(rowp + WS_OD2, d2);   // in the shadow of the MMAs
+            mbar_wait_sleep<RCMARL_WS_SLEEP3, RCMARL_WS_POLL>(mbar, mph);
             WS_TICK(7);
             mph ^= 1u;
             tmem_fence_after_sync();
@@ -438,8 +487,8 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
 }
 
 // ---- consumer warp cw (team cw / 4, member cw % 4): its team takes every second tile, the four members split the tile's
-// 43 three-row steps.  A buffer is held for a quarter of the time one warp would need, and two teams keep two buffers in
-// consumption while two are in production (ring of WS_NBUF = 5). ----
+// 43 three-row steps.  A buffer is held for a quarter of the time one warp would need, and each team alternates between the two
+// buffers of its producer group's ring. ----
 __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, uint32_t& nbase, f2 (&acc)[WS_ACC]) {
     const int lane = threadIdx.x & 31;
     const bool active = lane < 10 * WS_NG;
@@ -454,7 +503,7 @@ __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, ui
     for (int q = team; q < nq; q += WS_GROUPS, ++nbase) {
         const int b = team * WS_RING + (int)(nbase % WS_RING);
         const uint32_t use = nbase / WS_RING;
-        mbar_wait_sleep<0, 100>(S.full + b, use & 1u);
+        mbar_wait_sleep<0, RCMARL_WS_POLL_FULL>(S.full + b, use & 1u);
         const float* buf = S.bufs + (int64_t)b * WS_TILE_ROWS * WS_ROWF;
         // member m takes steps m, m + 4, ... of the 43 three-row steps: ten for everybody plus an eleventh whose rows may lie
         // beyond the tile (members 2 and 3: rows 128+), handled branch-free by clamping the row and zeroing its a-values.  All
@@ -555,7 +604,7 @@ __device__ __forceinline__ void ws_body(const GradParams& P, const rcmarl_grad_j
 #pragma unroll
         for (int j = 0; j <= HID; ++j) g3[j] = 0.f;
         float loss = 0.f;
-        ws_produce<NA, DIN>(S, Rw, job, y, gy, nq, nbase, mph, g3, loss);
+        ws_produce<NA, DIN, WS_SHADOW_SWEEP>(S, Rw, job, y, gy, nq, nbase, mph, g3, loss);
         named_barrier(WS_BAR_A, WS_THREADS);                          // every tile produced and consumed
         ws_park_producer(S, g3, loss);
     } else {

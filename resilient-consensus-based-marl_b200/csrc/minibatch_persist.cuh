@@ -240,7 +240,7 @@ __device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch,
 #pragma unroll
                 for (int k = 0; k <= HID; ++k) g3[k] = 0.f;
                 float loss = 0.f;
-                ws_produce<NA, DIN>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss);
+                ws_produce<NA, DIN, WS_SHADOW_STEP>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss);
                 named_barrier(WS_BAR_A, WS_THREADS);
                 ws_park_producer(S, g3, loss);
                 named_barrier(WS_BAR_B, WS_THREADS);
@@ -376,7 +376,7 @@ __device__ __forceinline__ void il_turn(const MbParams& P, WsShared S, int c, in
 #pragma unroll
         for (int k = 0; k <= HID; ++k) g3[k] = 0.f;
         float loss = 0.f;
-        ws_produce<NA, DIN>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss);
+        ws_produce<NA, DIN, WS_SHADOW_STEP>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss);
         named_barrier(WS_BAR_A, WS_THREADS);
         ws_park_producer(S, g3, loss);
     } else {

@@ -21,7 +21,7 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 for r in rows[2:]:
     print("----")
     d = dict(zip(hdr, r))
-    for w in WANT:
+    for w in WANT + [h for h in hdr if "pipe_tensor" in h and h.endswith("pct_of_peak_sustained_active")]:
         if w in d:
             print(f"{w} = {d[w]} {units[hdr.index(w)]}")
     try:

@@ -37,8 +37,8 @@ buf = (C.c_longlong * (64 * 16))()
 lib.rcmarl_debug_timeline.restype = C.c_int
 st = lib.rcmarl_debug_timeline(buf, 64 * 16)
 t = np.array(buf[:], np.int64).reshape(64, 16)
-names = ["claim buffer, x -> buffer, next loads, h1 -> buffer, split, STTM", "group barrier B", "L2 MMAs", "LDTM",
-         "lrelu, head, delta2 -> buffer, split (+ next x split), STTM", "group barrier C", "L3 + next L1 MMAs",
+names = ["h1 split, STTM", "group barrier B", "L2 MMAs (in their shadow: claim buffer, x / h1 -> buffer, next loads)", "LDTM",
+         "lrelu, head, delta2, split (+ next x split), STTM", "group barrier C", "L3 + next L1 MMAs (delta2 -> buffer)",
          "LDTM, delta1 -> buffer, arrive", "LDTM next h1"]
 t = t[:, :10]
 d = np.diff(t[8:60], axis=1)
