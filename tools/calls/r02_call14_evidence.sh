@@ -25,8 +25,8 @@ done
 echo "== launch list of one bench step"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-consensus > /dev/null 2>&1; wc -l gpurun_out/r02_launches.csv
 echo "== compute-sanitizer (memcheck, racecheck) over smoke()"
-timeout 600 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r02_sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r02_sanitizer_racecheck.log
+timeout 400 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r02_sanitizer_memcheck.log
+timeout 400 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r02_sanitizer_racecheck.log
 echo "== learning harness"
-timeout 1200 python tools/learning_harness.py 30 256 2>&1 | tail -30
+timeout 800 python tools/learning_harness.py 30 256 2>&1 | tail -30
 ls -la gpurun_out | tail -30
