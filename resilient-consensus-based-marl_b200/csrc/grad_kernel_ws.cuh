@@ -41,12 +41,14 @@ constexpr int WS_NBUF = WS_RING * WS_GROUPS;                  // 4: each stream 
                                                               // strictly ordered by ONE producer / consumer pair, which the
                                                               // parity waits of the mbarriers need (a shared ring let one stream
                                                               // run two uses ahead of the other and alias the parity)
-// floats per buffer row: x 16 | h1 20 + [1 0 0 0] | delta1 as two halves of 10 + 2 pad | delta2 likewise | 4 pad.
-// Every consumer operand is then a run of aligned LDS.128 (2 for an a-tile, 3 for a delta half) with no selects; 92 floats =
-// 23 x 16 bytes (odd), so the row-per-thread STS.128 of the producers and the row-group reads of the consumers spread over
-// the banks.
+// Buffer row = 23 x 16 bytes: the five 8-float a-tiles ([x | 1 0..] as two, [h1 | 1 0 0 0] as three) and the four 12-float delta
+// halves (delta1 / delta2 as 10 values + 2 zeros each), placed so that EVERY consumer LDS.128 is conflict-free: within a
+// quarter-warp the lanes (a-tile, delta half, row group) hit eight different 16-byte bank groups or the same address (found by
+// exhaustive search, tools/ws_bank_layout.py; the straightforward order x | h1 | delta1 | delta2 cost 26 wavefronts per step
+// instead of 20, and the shared-memory pipe was 64 % busy).  23 is odd, so the producers' row-per-thread STS.128 spread too.
 constexpr int WS_ROWF = 92;
-constexpr int WS_OX = 0, WS_OH1 = 16, WS_OD1 = 40, WS_OD2 = 64, WS_DHALF = 12;
+constexpr int WS_A0 = 32, WS_A1 = 76, WS_A2 = 84, WS_A3 = 68, WS_A4 = 24;   // float offsets of the a-tiles: x[0..7], x[8..15], h1[0..7], h1[8..15], [h1[16..19] 1 0 0 0]
+constexpr int WS_D1A = 40, WS_D1B = 12, WS_D2A = 56, WS_D2B = 0;            // delta1 halves, delta2 halves (float 52..55 is padding)
 constexpr int WS_TILE_ROWS = 128;
 constexpr int WS_NG = 3;                                      // row groups per consumer warp (5 a-tiles x 2 delta halves x 3 = 30 lanes)
 constexpr int WS_TEAM = 4;                                    // consumer warps that share one tile
@@ -106,6 +108,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         __nanosleep(NS);
         if (++polls > (1u << 23)) __trap();
     }
+}
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas knows the guarded region runs single-threaded and emits the
+// tcgen05 instructions (uniform-register operands) without a per-instruction election loop around each of them
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -171,13 +180,31 @@ __device__ __forceinline__ void ws_consume_row(const float* __restrict__ rp, int
 
 // a 20-vector as two halves of 10 values + 2 zeros each (the consumers' delta operands)
 template <int N>
-__device__ __forceinline__ void ws_store_halves(float* p, const float (&d)[N]) {
-    st4(p, d[0], d[1], d[2], d[3]);
-    st4(p + 4, d[4], d[5], d[6], d[7]);
-    st4(p + 8, d[8], d[9], 0.f, 0.f);
-    st4(p + 12, d[10], d[11], d[12], d[13]);
-    st4(p + 16, d[14], d[15], d[16], d[17]);
-    st4(p + 20, d[18], d[19], 0.f, 0.f);
+__device__ __forceinline__ void ws_store_halves(float* pa, float* pb, const float (&d)[N]) {
+    st4(pa, d[0], d[1], d[2], d[3]);
+    st4(pa + 4, d[4], d[5], d[6], d[7]);
+    st4(pa + 8, d[8], d[9], 0.f, 0.f);
+    st4(pb, d[10], d[11], d[12], d[13]);
+    st4(pb + 4, d[14], d[15], d[16], d[17]);
+    st4(pb + 8, d[18], d[19], 0.f, 0.f);
+}
+// this tile's features and first hidden layer -> the row's a-tiles
+template <int DIN>
+__device__ __forceinline__ void ws_file_inputs(float* rowp, const float (&xr)[DIN], const float (&h1)[HID]) {
+    st4(rowp + WS_A0, xr[0], xr[1], xr[2], xr[3]);
+    st4(rowp + WS_A0 + 4, xr[4], xr[5], xr[6], xr[7]);
+    if constexpr (DIN == 15) {
+        st4(rowp + WS_A1, xr[8], xr[9], xr[10], xr[11]);
+        st4(rowp + WS_A1 + 4, xr[12], xr[13], xr[14], 1.f);
+    } else {
+        st4(rowp + WS_A1, xr[8], xr[9], 1.f, 0.f);
+        st4(rowp + WS_A1 + 4, 0.f, 0.f, 0.f, 0.f);
+    }
+    st4(rowp + WS_A2, h1[0], h1[1], h1[2], h1[3]);
+    st4(rowp + WS_A2 + 4, h1[4], h1[5], h1[6], h1[7]);
+    st4(rowp + WS_A3, h1[8], h1[9], h1[10], h1[11]);
+    st4(rowp + WS_A3 + 4, h1[12], h1[13], h1[14], h1[15]);
+    st4(rowp + WS_A4, h1[16], h1[17], h1[18], h1[19]);
 }
 
 // inputs of row r of tile q of this CTA: features, target, and whether the row exists
@@ -231,7 +258,7 @@ __device__ __forceinline__ void ws_init(const WsShared& S) {
 // the constant column block [1 0 0 0] behind h1 of every buffer row (the bias row of the layer-2 weight gradient): written
 // once; the scratch use of the buffers at the end of a sweep overwrites it, so ws_pads() is repeated after every reduction
 __device__ __forceinline__ void ws_pads(const WsShared& S) {
-    for (int i = threadIdx.x; i < WS_NBUF * WS_TILE_ROWS; i += blockDim.x) st4(S.bufs + (int64_t)i * WS_ROWF + WS_OH1 + 20, 1.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < WS_NBUF * WS_TILE_ROWS; i += blockDim.x) st4(S.bufs + (int64_t)i * WS_ROWF + WS_A4 + 4, 1.f, 0.f, 0.f, 0.f);
 }
 
 // B operands from the staged parameters (canonical K-major, tf32 hi / lo): B1[n][k] = [W1; b1][k][n],
@@ -294,7 +321,6 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
     // columns: layer-1 operand hi / lo | layer-2 and backward operand hi / lo | layer-1 accumulator | layer-2 / backward acc.
     constexpr int CA1H = 0, CA1L = 16, CA2H = 32, CA2L = 56, CD1 = 80, CD2 = 112;
     const uint32_t idesc = umma_idesc_tf32(128, TC_N);
-    const bool issuer = (gwarp == 0) && (lane == 0);
     uint64_t* mbar = S.mma_bar + group;
     const SmemW W{S.sw};
 #if RCMARL_WS_TIMELINE
@@ -324,7 +350,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
         tmem_wait_st();
         tmem_fence_before_sync();
         named_barrier(1 + group, 128);
-        if (issuer) {
+        if (gwarp == 0 && elect_one()) {
             tmem_fence_after_sync();
             tc_issue<K1>(tmem + CD1, tmem + CA1H, tmem + CA1L, S.b1h, S.b1l, idesc);
             umma_commit(mbar);
@@ -352,17 +378,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
         const bool has_next = q + WS_GROUPS < nq;
         if constexpr ((SHADOW & 1) == 0) {
             mbar_wait_sleep<0, RCMARL_WS_POLL_EMPTY>(S.empty + b, ((nbase / WS_RING) & 1u) ^ 1u);
-            st4(rowp + WS_OX, xr[0], xr[1], xr[2], xr[3]);
-            st4(rowp + WS_OX + 4, xr[4], xr[5], xr[6], xr[7]);
-            if constexpr (DIN == 15) {
-                st4(rowp + WS_OX + 8, xr[8], xr[9], xr[10], xr[11]);
-                st4(rowp + WS_OX + 12, xr[12], xr[13], xr[14], 1.f);
-            } else {
-                st4(rowp + WS_OX + 8, xr[8], xr[9], 1.f, 0.f);
-                st4(rowp + WS_OX + 12, 0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
+            ws_file_inputs<DIN>(rowp, xr, h1);
         }
         const float tgt_q = tgt;
         const bool live_q = live;
@@ -382,7 +398,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             WS_TICK(1);
             named_barrier(1 + group, 128);
             WS_TICK(2);
-            if (issuer) {
+            if (gwarp == 0 && elect_one()) {
                 tmem_fence_after_sync();
                 tc_issue<24>(tmem + CD2, tmem + CA2H, tmem + CA2L, S.b2h, S.b2l, idesc);
                 umma_commit(mbar);
@@ -392,17 +408,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             // rest of this round trip and the output-layer arithmetic to arrive.  None of it is on the path to the next issue.
             if constexpr ((SHADOW & 1) != 0) {
             mbar_wait_sleep<0, RCMARL_WS_POLL_EMPTY>(S.empty + b, ((nbase / WS_RING) & 1u) ^ 1u);
-            st4(rowp + WS_OX, xr[0], xr[1], xr[2], xr[3]);
-            st4(rowp + WS_OX + 4, xr[4], xr[5], xr[6], xr[7]);
-            if constexpr (DIN == 15) {
-                st4(rowp + WS_OX + 8, xr[8], xr[9], xr[10], xr[11]);
-                st4(rowp + WS_OX + 12, xr[12], xr[13], xr[14], 1.f);
-            } else {
-                st4(rowp + WS_OX + 8, xr[8], xr[9], 1.f, 0.f);
-                st4(rowp + WS_OX + 12, 0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int qq = 0; qq < 5; ++qq) st4(rowp + WS_OH1 + 4 * qq, h1[4 * qq], h1[4 * qq + 1], h1[4 * qq + 2], h1[4 * qq + 3]);
+            ws_file_inputs<DIN>(rowp, xr, h1);
             }
             if constexpr ((SHADOW & 2) != 0) {
                 if (has_next) ws_fetch<NA, DIN>(Rw, job, y, gy, q + WS_GROUPS, r, xr, tgt, live);
@@ -434,7 +440,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
         }
         // ---------------- backward-data of this tile + layer 1 of the stream's next tile ----------------
         {
-            if constexpr ((SHADOW & 4) == 0) ws_store_halves(rowp + WS_OD2, d2);
+            if constexpr ((SHADOW & 4) == 0) ws_store_halves(rowp + WS_D2A, rowp + WS_D2B, d2);
             ws_store_operand<24>(tlane, CA2H, CA2L, d2);
             if (has_next) {                                           // xr holds the next tile's features by now
                 float x[K1];
@@ -449,13 +455,13 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             WS_TICK(5);
             named_barrier(1 + group, 128);
             WS_TICK(6);
-            if (issuer) {
+            if (gwarp == 0 && elect_one()) {
                 tmem_fence_after_sync();
                 tc_issue<24>(tmem + CD2, tmem + CA2H, tmem + CA2L, S.b3h, S.b3l, idesc);
                 if (has_next) tc_issue<K1>(tmem + CD1, tmem + CA1H, tmem + CA1L, S.b1h, S.b1l, idesc);
                 umma_commit(mbar);
             }
-            if constexpr ((SHADOW & 4) != 0) ws_store_halves(rowp + WS_OD2, d2);   // in the shadow of the MMAs
+            if constexpr ((SHADOW & 4) != 0) ws_store_halves(rowp + WS_D2A, rowp + WS_D2B, d2);   // in the shadow of the MMAs
             mbar_wait_sleep<RCMARL_WS_SLEEP3, RCMARL_WS_POLL>(mbar, mph);
             WS_TICK(7);
             mph ^= 1u;
@@ -466,7 +472,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             float d1[HID];
 #pragma unroll
             for (int i = 0; i < HID; ++i) d1[i] = __uint_as_float(u[i]) * lrelu_grad_from_out(h1[i]);
-            ws_store_halves(rowp + WS_OD1, d1);
+            ws_store_halves(rowp + WS_D1A, rowp + WS_D1B, d1);
             __syncwarp();
             if (lane == 0) mbar_arrive(S.full + b);                   // release: this warp's 32 rows of the buffer are complete
             WS_TICK(8);
@@ -495,8 +501,8 @@ __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, ui
     const int combo = active ? lane % 10 : 0;                         // (a-tile, delta half)
     const int atile = combo % 5, half = combo / 5;
     const int grp = active ? lane / 10 : 0;
-    const int acol = 8 * atile;                                       // x: 0..15, [h1 | 1 0 0 0]: 16..39
-    const int dcol = (atile < 2 ? WS_OD1 : WS_OD2) + WS_DHALF * half;
+    const int acol = atile == 0 ? WS_A0 : atile == 1 ? WS_A1 : atile == 2 ? WS_A2 : atile == 3 ? WS_A3 : WS_A4;
+    const int dcol = atile < 2 ? (half ? WS_D1B : WS_D1A) : (half ? WS_D2B : WS_D2A);   // x-tiles pair with delta1, h1-tiles with delta2
     const int team = cw / WS_TEAM, member = cw % WS_TEAM;
     constexpr int FULL_STEPS = WS_TILE_ROWS / WS_NG;                  // 42 (+ rows 126, 127 as step 42)
     static_assert(WS_CONS / WS_TEAM == WS_GROUPS, "one consumer team per producer group");
