@@ -58,6 +58,9 @@ constexpr int WS_ACC = 40;                                    // packed accumula
 // were the bottleneck -- two narrower consumer warps per scheduler cover each other's latencies)
 // back-off of a producer group waiting for its MMAs: first sleep after the layer-2 batch (9 MMAs) / after the merged backward +
 // next-layer-1 batch (15 MMAs), then the poll interval, in ns (a sweep of 0 .. 450 ns changed nothing, profiles/r02_kernel_experiments.md)
+#ifndef RCMARL_WS_SPLIT_TRUNC
+#define RCMARL_WS_SPLIT_TRUNC 1
+#endif
 #ifndef RCMARL_WS_SLEEP2
 #define RCMARL_WS_SLEEP2 120
 #endif
@@ -75,7 +78,7 @@ constexpr int WS_ACC = 40;                                    // packed accumula
 #define RCMARL_WS_SHADOW_SWEEP 0
 #endif
 #ifndef RCMARL_WS_SHADOW_STEP
-#define RCMARL_WS_SHADOW_STEP 7
+#define RCMARL_WS_SHADOW_STEP 6
 #endif
 constexpr int WS_SHADOW_SWEEP = RCMARL_WS_SHADOW_SWEEP, WS_SHADOW_STEP = RCMARL_WS_SHADOW_STEP;
 #ifndef RCMARL_WS_POLL_EMPTY                                   // producers waiting for a free buffer / consumers for a full one
@@ -130,8 +133,15 @@ __device__ __forceinline__ void ws_store_operand(uint32_t tlane, int col_hi, int
         uint32_t h[8], l[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            // round-to-nearest (ties away) to 10 mantissa bits, as cvt.rna.tf32.f32 without its inf / NaN guard: 2 integer ops
+            // hi = the value truncated to tf32 (one LOP; the tensor core ignores the 13 low mantissa bits anyway), lo = value - hi
+            // (exact).  Rounding hi to nearest (+ 0x1000 first) halves |lo| but costs a third operation on each of the 64 operand
+            // elements of a row: one product is within 2.2e-7 of fp64 either way (tools/experiments/tf32x3_error.py), the
+            // gradient sweep 3 % faster (profiles/r02_kernel_experiments.md).  -DRCMARL_WS_SPLIT_TRUNC=0 restores the rounding.
+#if RCMARL_WS_SPLIT_TRUNC
+            h[k] = __float_as_uint(v[8 * c + k]) & 0xFFFFE000u;
+#else
             h[k] = (__float_as_uint(v[8 * c + k]) + 0x1000u) & 0xFFFFE000u;
+#endif
             l[k] = __float_as_uint(v[8 * c + k] - __uint_as_float(h[k]));
         }
         tmem_st8(tlane + col_hi + 8 * c, h);
@@ -301,9 +311,12 @@ __device__ __forceinline__ int ws_tile_count(int64_t n_rows, int y, int gy) {
 #endif
 #if RCMARL_WS_TIMELINE
 __device__ long long g_ws_timeline[64 * 16];
+__device__ long long g_mb_timeline[64 * 16];                  // persistent mini-batch kernel: [step][stage], CTA 0 / thread 0
+#define MB_TICK(k) do { if (mb_tl_on && mb_tl_step < 64) g_mb_timeline[mb_tl_step * 16 + (k)] = clock64(); } while (0)
 #define WS_TICK(k) do { if (tl_on && tl_tile < 64) g_ws_timeline[tl_tile * 16 + (k)] = clock64(); } while (0)
 #else
 #define WS_TICK(k) do { } while (0)
+#define MB_TICK(k) do { } while (0)
 #endif
 
 // ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  nbase = tiles this stream pushed through its ring in
@@ -530,7 +543,10 @@ __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, ui
 // ---- end of a sweep: every thread passes (A), the roles park their sums in the (now idle) tile buffers, (B), and the CTA
 // adds them up in a fixed order; store(i, v) receives the sums for the packed parameters i = 0 .. NP-1 and the loss as NP ----
 __device__ __forceinline__ float* ws_red(const WsShared& S) { return S.bufs; }
-__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.bufs + WS_CONS * 32 * (2 * WS_ACC); }
+// floats per parked consumer lane: 80 sums + 4 pad = 21 x 16 bytes (odd), so the lanes' STS.128 spread over the bank groups
+// (at 80 floats the eight lanes of a quarter-warp hit two bank groups: 4-way conflicts on every store of the epilogue)
+constexpr int WS_PARK = 2 * WS_ACC + 4;
+__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.bufs + WS_CONS * 32 * WS_PARK; }
 __device__ __forceinline__ void ws_park_producer(const WsShared& S, const float (&g3)[HID + 1], float loss) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* red3 = ws_red3(S);
@@ -544,7 +560,7 @@ __device__ __forceinline__ void ws_park_producer(const WsShared& S, const float 
 }
 __device__ __forceinline__ void ws_park_consumer(const WsShared& S, int cw, const f2 (&acc)[WS_ACC]) {
     const int lane = threadIdx.x & 31;
-    float4* dst = reinterpret_cast<float4*>(ws_red(S) + (cw * 32 + lane) * (2 * WS_ACC));
+    float4* dst = reinterpret_cast<float4*>(ws_red(S) + (cw * 32 + lane) * WS_PARK);
 #pragma unroll
     for (int e = 0; e < WS_ACC / 2; ++e) {
         float4 v;
@@ -567,7 +583,7 @@ __device__ __forceinline__ void ws_cta_sums(const WsShared& S, ST store) {
             float s = 0.f;
             for (int c = 0; c < WS_CONS; ++c)
 #pragma unroll
-                for (int g = 0; g < WS_NG; ++g) s += red[(c * 32 + g * 10 + half * 5 + t) * (2 * WS_ACC) + slot];
+                for (int g = 0; g < WS_NG; ++g) s += red[(c * 32 + g * 10 + half * 5 + t) * WS_PARK + slot];
             store(idx, s);
         }
     }

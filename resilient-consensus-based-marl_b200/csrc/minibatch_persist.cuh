@@ -59,6 +59,7 @@ __device__ __forceinline__ uint2 poll_cell(const uint2* cell, uint32_t seq, uint
                 __threadfence_system();
                 __trap();
             }
+            __nanosleep(RCMARL_CELL_POLL_NS);           // spinning CTAs must not crowd the writers out of the L2 queues
             x = ld_cell(cell);
         } while (x.y != seq);
     }
@@ -170,11 +171,12 @@ struct MbStepCtx {
 // sums of this step -> level-1 cells -> slice owner's CTA-ordered sum -> level-2 cells -> SGD step on the shared-memory copy
 template <int DIN>
 __device__ __forceinline__ void mb_step_tail(const WsShared& S, const MbStepCtx& c, uint32_t s1, uint32_t s2, float coef,
-                                             bool first_epoch, float& loss_acc) {
+                                             bool first_epoch, float& loss_acc, bool mb_tl_on = false, int mb_tl_step = 0) {
     constexpr int NP = param_count(DIN, 1);
     const int warp = threadIdx.x >> 5;
     uint2* my1 = c.my1;
     ws_cta_sums<DIN>(S, [my1, s1](int i, float v) { st_cell(my1 + i, v, s1); });
+    MB_TICK(5);
     for (int base = c.sl_begin + warp * c.e_per_warp; base < c.sl_end; base += WS_WARPS * c.e_per_warp) {
         const int i = base + c.e_local;
         float s = 0.f;
@@ -185,11 +187,13 @@ __device__ __forceinline__ void mb_step_tail(const WsShared& S, const MbStepCtx&
         for (int o = 1; o < c.S; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (i < c.sl_end && c.sgroup == 0) comm_push(*c.comm, c.off2 + i, s, s2);
     }
+    MB_TICK(6);
     for (int i = threadIdx.x; i <= NP; i += WS_THREADS) {
         const float tot = comm_wait_total(*c.comm, c.off2 + i, s2);
         if (i < NP) S.sw[i] = S.sw[i] - coef * tot;
         else if (first_epoch) loss_acc += c.loss_coef * tot;
     }
+    MB_TICK(7);
 }
 
 template <int NA, int DIN>
@@ -227,10 +231,22 @@ __device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch,
 
     if (warp < 4 * WS_GROUPS) {
         uint32_t mph = 0;
+#if RCMARL_WS_TIMELINE
+        const bool mb_tl_on = blockIdx.x == 0 && threadIdx.x == 0;
+        int mb_tl_step = -1;
+#else
+        constexpr bool mb_tl_on = false;
+        constexpr int mb_tl_step = 0;
+#endif
         for (int e = 0; e < P.epochs; ++e) {
             for (int b = 0; b < nb; ++b, ++seq1, ++seq2) {
+#if RCMARL_WS_TIMELINE
+                ++mb_tl_step;
+#endif
+                MB_TICK(0);
                 ws_build_operands<DIN>(S);
                 named_barrier(WS_BAR_C, WS_THREADS);
+                MB_TICK(1);
                 tmem_fence_after_sync();
                 const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
                 Rw.n_rows = (int64_t)cnt * Rw.n_envs;
@@ -241,11 +257,15 @@ __device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch,
                 for (int k = 0; k <= HID; ++k) g3[k] = 0.f;
                 float loss = 0.f;
                 ws_produce<NA, DIN, WS_SHADOW_STEP>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss);
+                MB_TICK(2);
                 named_barrier(WS_BAR_A, WS_THREADS);
+                MB_TICK(3);
                 ws_park_producer(S, g3, loss);
                 named_barrier(WS_BAR_B, WS_THREADS);
-                mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / ((float)Rw.n_rows * world), e == 0, loss_acc);
+                MB_TICK(4);
+                mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / ((float)Rw.n_rows * world), e == 0, loss_acc, mb_tl_on, mb_tl_step);
                 named_barrier(WS_BAR_D, WS_THREADS);                  // new parameters visible; scratch reusable
+                MB_TICK(8);
             }
         }
     } else {

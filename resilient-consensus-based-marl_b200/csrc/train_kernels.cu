@@ -970,6 +970,12 @@ int rcmarl_debug_timeline(long long* out_host, int n) {
     RC_CUDA(cudaMemcpyFromSymbol(out_host, g_ws_timeline, sizeof(long long) * n));
     return RCMARL_OK;
 }
+/* same for the persistent mini-batch kernel: [64 steps][16 ticks] of CTA 0 / thread 0 */
+int rcmarl_debug_timeline_mb(long long* out_host, int n) {
+    if (!out_host || n < 1 || n > 64 * 16) return RCMARL_ERR_ARG;
+    RC_CUDA(cudaMemcpyFromSymbol(out_host, g_mb_timeline, sizeof(long long) * n));
+    return RCMARL_OK;
+}
 #endif
 
 int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs, void* ws, int64_t ws_bytes,

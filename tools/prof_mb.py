@@ -33,5 +33,19 @@ for _ in range(reps):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 steps = tr.mb_epochs * ((tr.t_filled + tr.mb_times - 1) // tr.mb_times)
+if os.environ.get("RCMARL_MB_TIMELINE") == "1":            # debug build (make variant_tl): per-step stage timeline of CTA 0
+    import ctypes as C
+    lib = L.lib()
+    buf = (C.c_longlong * (64 * 16))()
+    lib.rcmarl_debug_timeline_mb.restype = C.c_int
+    st = lib.rcmarl_debug_timeline_mb(buf, 64 * 16)
+    t = np.array(buf[:], np.int64).reshape(64, 16)[8:60, :9]
+    names = ["operand rebuild + barrier", "own tiles produced (sweep)", "barrier A (all tiles consumed)", "park + barrier B",
+             "CTA sums -> level-1 cells", "gather (poll level-1, publish level-2)", "apply (poll level-2, SGD)", "barrier D"]
+    d = np.diff(t, axis=1)
+    per = np.diff(t[:, 0])
+    print("status", st, "step period (cycles): mean", per.mean(), "min", per.min(), "max", per.max())
+    for k, n in enumerate(names):
+        print(f"{n:42s} mean {d[:, k].mean():8.0f}  min {d[:, k].min():6d}  max {d[:, k].max():6d}")
 print(f"minibatch chain: n_envs={N} T={tr.t_filled} steps={steps} persistent={tr.mb_cells is not None} "
       f"ms_per_call={np.median(ts):.3f} us_per_step={1e3 * np.median(ts) / steps:.2f} (all: {[round(t, 2) for t in ts]})")
