@@ -321,9 +321,18 @@ __device__ long long g_mb_timeline[64 * 16];                  // persistent mini
 
 // ---- producer: tiles q = group, group + WS_GROUPS, ... of this sweep.  nbase = tiles this stream pushed through its ring in
 // earlier sweeps of the same kernel (buffer index and barrier parities continue across sweeps); advanced here. ----
-template <int NA, int DIN, int SHADOW>
+// inputs of a stream's first tile, loaded ahead of the sweep (the persistent mini-batch kernel fetches the next step's first
+// rows before the step's reduction / exchange, so the sweep does not start with an exposed DRAM round trip)
+template <int DIN>
+struct WsFirst {
+    float x[DIN];
+    float tgt;
+    bool live;
+};
+template <int NA, int DIN, int SHADOW, bool PREFETCHED = false>
 __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows& Rw, const rcmarl_grad_job& job, int y, int gy,
-                                           int nq, uint32_t& nbase, uint32_t& mph, float (&g3)[HID + 1], float& loss) {
+                                           int nq, uint32_t& nbase, uint32_t& mph, float (&g3)[HID + 1], float& loss,
+                                           const WsFirst<DIN>* first = nullptr) {
     static_assert((SHADOW & 3) != 1, "the next tile's loads overwrite the features the deferred filing still needs");
     constexpr int K1 = 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,7 +361,14 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
     float tgt = 0.f;
     bool live = false;
     float h1[HID];
-    ws_fetch<NA, DIN>(Rw, job, y, gy, group, r, xr, tgt, live);
+    if constexpr (PREFETCHED) {
+#pragma unroll
+        for (int k = 0; k < DIN; ++k) xr[k] = first->x[k];
+        tgt = first->tgt;
+        live = first->live;
+    } else {
+        ws_fetch<NA, DIN>(Rw, job, y, gy, group, r, xr, tgt, live);
+    }
     {   // ---------------- prologue: layer 1 of the stream's first tile ----------------
         float x[K1];
 #pragma unroll

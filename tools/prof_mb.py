@@ -39,13 +39,21 @@ if os.environ.get("RCMARL_MB_TIMELINE") == "1":            # debug build (make v
     buf = (C.c_longlong * (64 * 16))()
     lib.rcmarl_debug_timeline_mb.restype = C.c_int
     st = lib.rcmarl_debug_timeline_mb(buf, 64 * 16)
-    t = np.array(buf[:], np.int64).reshape(64, 16)[8:60, :9]
-    names = ["operand rebuild + barrier", "own tiles produced (sweep)", "barrier A (all tiles consumed)", "park + barrier B",
-             "CTA sums -> level-1 cells", "gather (poll level-1, publish level-2)", "apply (poll level-2, SGD)", "barrier D"]
+    T = np.array(buf[:], np.int64).reshape(64, 16)[8:60]
+    order = [0, 1, 2, 3, 9, 4, 5, 6, 7, 8]                   # producer thread 0 (tick 9 sits between 3 and 4)
+    names = ["operand rebuild + barrier", "own tiles produced (sweep) + next step's first loads issued", "barrier A (all tiles consumed)",
+             "park (warp sums of the output-layer gradient)", "barrier B", "CTA sums -> level-1 cells",
+             "gather (poll level-1, publish level-2)", "apply (poll level-2, SGD)", "barrier D"]
+    t = T[:, order]
     d = np.diff(t, axis=1)
-    per = np.diff(t[:, 0])
+    per = np.diff(T[:, 0])
     print("status", st, "step period (cycles): mean", per.mean(), "min", per.min(), "max", per.max())
     for k, n in enumerate(names):
-        print(f"{n:42s} mean {d[:, k].mean():8.0f}  min {d[:, k].min():6d}  max {d[:, k].max():6d}")
+        print(f"{n:62s} mean {d[:, k].mean():8.0f}  min {d[:, k].min():6d}  max {d[:, k].max():6d}")
+    c = T[:, [1, 10, 11, 12]]                                # first consumer thread, relative to the producer's tick 1
+    for n, a, b in (("consumer: last tile consumed, after the operands barrier", 0, 1), ("consumer: wait at barrier A", 1, 2),
+                    ("consumer: park", 2, 3)):
+        v = c[:, b] - c[:, a]
+        print(f"{n:62s} mean {v.mean():8.0f}  min {v.min():6d}  max {v.max():6d}")
 print(f"minibatch chain: n_envs={N} T={tr.t_filled} steps={steps} persistent={tr.mb_cells is not None} "
       f"ms_per_call={np.median(ts):.3f} us_per_step={1e3 * np.median(ts) / steps:.2f} (all: {[round(t, 2) for t in ts]})")
