@@ -123,6 +123,13 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// t * LeakyReLU'(pre-activation), decided on the layer's OUTPUT h (same sign): a compare and a predicated multiply instead of
+// compare + select + multiply (40 of these per buffer row)
+__device__ __forceinline__ float ws_times_lrelu_grad(float t, float h) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\t@!p mul.f32 %0, %0, %2;\n\t}" : "+f"(t) : "f"(h), "f"(SLOPE));
+    return t;
+}
+
 // tf32 hi / lo halves of this thread's K operand values -> TMEM columns [col_hi, col_hi + K) and [col_lo, col_lo + K) of its
 // lane, 8 columns at a time (16 live temporaries instead of 2 K: the producers run on a 128-register budget)
 template <int K>
@@ -462,7 +469,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
 #pragma unroll
             for (int j = 0; j < HID; ++j) {
                 g3[j] = fmaf(h2[j], e, g3[j]);
-                d2[j] = W.s(off_W3(DIN) + j) * e * lrelu_grad_from_out(h2[j]);
+                d2[j] = ws_times_lrelu_grad(W.s(off_W3(DIN) + j) * e, h2[j]);
             }
             g3[HID] += e;
             d2[20] = 0.f; d2[21] = 0.f; d2[22] = 0.f; d2[23] = 0.f;
@@ -500,7 +507,7 @@ __device__ __forceinline__ void ws_produce(const WsShared& S, const rcmarl_rows&
             tmem_wait_ld();
             float d1[HID];
 #pragma unroll
-            for (int i = 0; i < HID; ++i) d1[i] = __uint_as_float(u[i]) * lrelu_grad_from_out(h1[i]);
+            for (int i = 0; i < HID; ++i) d1[i] = ws_times_lrelu_grad(__uint_as_float(u[i]), h1[i]);
             ws_store_halves(rowp + WS_D1A, rowp + WS_D1B, d1);
             __syncwarp();
             if (lane == 0) mbar_arrive(S.full + b);                   // release: this warp's 32 rows of the buffer are complete

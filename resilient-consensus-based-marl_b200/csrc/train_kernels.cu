@@ -260,6 +260,10 @@ struct TeamParams {
     float* partial;
     int32_t n_jobs;
     int32_t stride;
+    // jobs of THIS launch (blockIdx.x -> job index).  rcmarl_team launches the team-reward nets (15 inputs) and the critics
+    // (10 inputs) separately: the loop body of one instantiation is ~24 KB of SASS, two of them resident on an SM overflow the
+    // 32 KB instruction cache (28 % of the stall samples were "no instruction", profiles/r02_ncu_other_kernels.md)
+    int32_t job_list[RCMARL_MAX_JOBS];
 };
 constexpr int TEAM_N = HID + 2;  // 20 weights + bias numerators + diagnostic loss
 
@@ -353,14 +357,14 @@ __device__ __forceinline__ void team_body(const TeamParams& P, const rcmarl_team
     if (threadIdx.x < TEAM_N) {
         float s = 0.f;
         for (int w = 0; w < nwarps; ++w) s += red[w * TEAM_N + threadIdx.x];
-        P.partial[((int64_t)blockIdx.y * P.n_jobs + blockIdx.x) * P.stride + threadIdx.x] = s;
+        P.partial[((int64_t)blockIdx.y * P.n_jobs + P.job_list[blockIdx.x]) * P.stride + threadIdx.x] = s;
     }
 }
 
 template <int NA>
 __global__ void __launch_bounds__(128) team_kernel(const __grid_constant__ TeamParams P) {
     extern __shared__ __align__(16) float smem[];
-    const rcmarl_team_job& job = P.jobs[blockIdx.x];
+    const rcmarl_team_job& job = P.jobs[P.job_list[blockIdx.x]];
     const bool sa = job.kind == RCMARL_IN_SA;
     if (job.n_in <= 4) {
         if (sa) team_body<NA, 3 * NA, 4>(P, job, smem); else team_body<NA, 2 * NA, 4>(P, job, smem);
@@ -520,10 +524,10 @@ static int grad_chunks_per_cta(int loss_mode) {
 }
 
 template <int NA>
-static int launch_team(const TeamParams& P, int gy, cudaStream_t st) {
+static int launch_team(const TeamParams& P, int n_list, int gy, cudaStream_t st) {
     const size_t smem = sizeof(float) * (round4(param_count(3 * NA, 1)) + RCMARL_MAX_NEIGHBOURS * 24 + 8 * TEAM_N);
     if (set_smem(team_kernel<NA>, smem)) return RCMARL_ERR_CUDA;
-    team_kernel<NA><<<dim3(P.n_jobs, gy), 128, smem, st>>>(P);
+    team_kernel<NA><<<dim3(n_list, gy), 128, smem, st>>>(P);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -999,21 +1003,38 @@ int rcmarl_team(const rcmarl_rows* rows, const rcmarl_team_job* jobs, int n_jobs
         Q.sums[j] = q.sums;
         Q.n[j] = q.sums ? TEAM_N : 0;
     }
-    const int gy = grid_y_for((rows->n_rows + 255) / 256, n_jobs, 3);   // 128 threads x 2 rows; 3 CTAs/SM resident
+    // one launch per input kind (see TeamParams::job_list); each fills the GPU on its own: 128 threads x 2 rows, 3 CTAs / SM
+    int gy_of[RCMARL_MAX_JOBS], gy_max = 0;
+    int lists[2][RCMARL_MAX_JOBS], n_list[2] = {0, 0};
+    for (int j = 0; j < n_jobs; ++j) {
+        const int g = jobs[j].kind == RCMARL_IN_SA ? 0 : 1;
+        lists[g][n_list[g]++] = j;
+    }
+    for (int g = 0; g < 2; ++g) {
+        if (!n_list[g]) continue;
+        const int gy = grid_y_for((rows->n_rows + 255) / 256, n_list[g], 3);
+        for (int k = 0; k < n_list[g]; ++k) gy_of[lists[g][k]] = gy;
+        gy_max = gy > gy_max ? gy : gy_max;
+    }
     if (any_sums) {
-        if (!ws || (int64_t)gy * n_jobs * TEAM_N * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
+        if (!ws || (int64_t)gy_max * n_jobs * TEAM_N * (int64_t)sizeof(float) > ws_bytes) return RCMARL_ERR_WORKSPACE;
     }
     P.partial = (float*)ws;
     P.n_jobs = n_jobs;
     P.stride = TEAM_N;
     cudaStream_t st = (cudaStream_t)stream;
-    int e = NA == 5 ? launch_team<5>(P, gy, st) : launch_team<16>(P, gy, st);
-    if (e) return e;
+    for (int g = 0; g < 2; ++g) {
+        if (!n_list[g]) continue;
+        for (int k = 0; k < n_list[g]; ++k) P.job_list[k] = lists[g][k];
+        const int gy = gy_of[lists[g][0]];
+        const int e = NA == 5 ? launch_team<5>(P, n_list[g], gy, st) : launch_team<16>(P, n_list[g], gy, st);
+        if (e) return e;
+    }
     if (any_sums) {
         Q.partial = (const float*)ws;
         Q.slots.step = n_jobs;                    // team_kernel writes its partials [y][job] interleaved
         Q.slots.stride = TEAM_N;
-        for (int j = 0; j < n_jobs; ++j) { Q.slots.first[j] = j; Q.slots.count[j] = gy; }
+        for (int j = 0; j < n_jobs; ++j) { Q.slots.first[j] = j; Q.slots.count[j] = gy_of[j]; }
         if (comm_bound()) {
             ReduceCommParams C;
             if (!comm_next(&C.comm, (int64_t)n_jobs * TEAM_N)) return RCMARL_ERR_ARG;
