@@ -117,8 +117,8 @@ class ClockSampler:
 
 
 def grad_traffic(workload_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one grad_kernel launch from the committed `ncu --set full`
-    capture (profiles/r01_grad_traffic.json); only valid for the workload it was captured on."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one full-batch gradient launch from the committed `ncu --set full`
+    capture (profiles/r02_grad_traffic.json); only valid for the workload it was captured on."""
     if workload_name != "C2":
         return None
     for name in ("r02_grad_traffic.json", "r01_grad_traffic.json"):
@@ -361,7 +361,10 @@ def main():
             t_tot += float(np.sum(prof["minibatch_sgd"]))
             f_tot += flops_call * len(prof["minibatch_sgd"])
         tf_w = f_tot / (t_tot * 1e-3) / 1e12
-        roof = dict(kernel=f"grad_kernel<{tr.NA},MSE> (fused MLP forward/backward; rcmarl_grad + rcmarl_minibatch_fit)",
+        kname = ("grad_kernel_ws + mb_persist_ws_kernel (warp-specialised tcgen05 3xTF32 + FFMA2 fused MLP forward/backward; "
+                 "rcmarl_grad + rcmarl_minibatch_fit)") if tr.NA == 5 else \
+            f"grad_kernel<{tr.NA},MSE> (FFMA2 fused MLP forward/backward; rcmarl_grad + rcmarl_minibatch_fit)"
+        roof = dict(kernel=kname,
                     bound="fp32", achieved=tf_w, peak=fp32_peak, unit="TFLOP/s", frac=tf_w / fp32_peak,
                     frac_is="time-weighted over both regimes of the kernel (full-batch fits + mini-batch chains)",
                     share_of_step=t_tot / ms, traffic=grad_traffic(args.workload),

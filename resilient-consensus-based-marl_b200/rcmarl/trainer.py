@@ -355,7 +355,8 @@ class Trainer:
                 self._timed("team", ops.team, rows_all, team_jobs, self.ws)
                 self._allreduce(self.sums_team[:2 * len(coop)])
                 ops.sgd_apply(team_apply)
-                self.launches += 4
+                # consensus_hidden + team_kernel per input kind (critic / team-reward nets) + reduce + sgd
+                self.launches += 3 + len({j.kind for j in team_jobs})
 
         # ---------------- III) actor updates (:149-153) on the newest block
         Ta = min(self.block, T)
