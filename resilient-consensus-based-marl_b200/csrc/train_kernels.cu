@@ -572,7 +572,7 @@ static int grid_y_for(int64_t work_items, int n_jobs, int ctas_per_sm) {
 // finishes last gets the next CTA.  Measured on B200 (profiles/r01_late_variants.md, run 3): -1.2 % / -2.2 % on isolated
 // full-batch / mini-batch launches but +1.5 % on the C2 update round, so it stays opt-in until that is understood.
 #ifndef RCMARL_MB_EQUAL_SHARES
-#define RCMARL_MB_EQUAL_SHARES 1
+#define RCMARL_MB_EQUAL_SHARES 0
 #endif
 #ifndef RCMARL_BALANCED_GRID_DEFAULT
 #define RCMARL_BALANCED_GRID_DEFAULT 0
@@ -920,8 +920,9 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
         c.target_stride = q.target_stride; c.lr = sjobs[j].coef > 0.f ? sjobs[j].coef : lr;
         c.loss_coef = sjobs[j].loss_coef; c.kind = q.kind; c.loss_accumulate = sjobs[j].loss_accumulate;
 #if RCMARL_GRAD_WS && RCMARL_MB_EQUAL_SHARES
-        // on the tensor-core core a row costs the same for both nets (the layer-1 operand is 16 wide either way), so the chains
-        // get equal shares (49 / 49 / 50 CTAs at C2: at most 21 tiles per CTA instead of 22 with the FFMA2 cost model's 48 / 52 / 48)
+        // experiment (off): equal shares on the tensor-core core (50 / 49 / 49 CTAs at C2 instead of the cost model's 48 / 52 / 48).
+        // Measured slower, 41.0 vs 40.1 us per step: the team-reward chain (15 inputs to load per row) is the slower one per tile
+        // and wants its 20-tile share (profiles/r02_kernel_experiments.md)
         cost[j] = NA == 5 ? 1 : grad_job_cost(NA, q.kind, RCMARL_LOSS_MSE);
 #else
         cost[j] = grad_job_cost(NA, q.kind, RCMARL_LOSS_MSE);
