@@ -47,6 +47,21 @@ struct Track {
         for (int i = 0; i < H; ++i) { const float hi = fmaxf(large[i], c); c = fminf(large[i], c); large[i] = hi; }
         large[H] = fmaxf(large[H], c);
     }
+    // Two values at once for H == 1: sort the pair, then the two smallest of {small[0] <= small[1], lo <= hi} are
+    // min(small[0], lo) and min3(small[1], hi, max(small[0], lo)); likewise the two largest.  8 min / max per pair (three-input
+    // FMNMX3 for the second order statistic) instead of 12, same values and the same summation order as two push() calls.
+    __device__ __forceinline__ void push2(float a, float b) {
+        static_assert(H == 1, "pair update is written for H == 1");
+        sum += a;
+        sum += b;
+        const float lo = fminf(a, b), hi = fmaxf(a, b);
+        const float m = fmaxf(small[0], lo);
+        small[0] = fminf(small[0], lo);
+        asm("min.f32 %0, %0, %1, %2;" : "+f"(small[1]) : "f"(hi), "f"(m));
+        const float w = fminf(large[0], hi);
+        large[0] = fmaxf(large[0], hi);
+        asm("max.f32 %0, %0, %1, %2;" : "+f"(large[1]) : "f"(lo), "f"(w));
+    }
     __device__ __forceinline__ void window(float own, float& lo, float& hi) const {
         lo = fminf(small[H], own);
         hi = fmaxf(large[H], own);
@@ -157,6 +172,11 @@ __global__ void __launch_bounds__(256) clip_mean_vec_kernel(const float* __restr
                 for (int u = 0; u < 8; ++u) g[u] = v[u][q];
                 push_group8<H>(t[q], g);
             }
+        } else if constexpr (H == 1) {
+#pragma unroll
+            for (int u = 0; u < CM_UNROLL; u += 2)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) t[q].push2(v[u][q], v[u + 1][q]);
         } else {
 #pragma unroll
             for (int u = 0; u < CM_UNROLL; ++u)
