@@ -341,172 +341,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mb_persist_ws_kernel(const __gr
     else mb_body_ws<5, 10>(P, ch, j, smem, y, gy);
 }
 
-// =====================================================================================================================
-// Interleaved chains (2 .. MB_IL_MAX chains, n_agents = 5): EVERY CTA serves EVERY chain, one chain per turn, round robin.
-// A chain's step then needs no waiting at all: its sums leave as level-1 cells at the end of its turn, the slice owners
-// add them up one turn later (while the next chain is being swept), and the SGD step is applied when the chain's turn comes
-// round again -- by then the level-2 cells have long arrived.  In the exclusive mapping above (each chain on its own third of
-// the CTAs) every one of the 9 400 sequential steps of an update round exposed two L2 round trips, the CTA reduction and the
-// pipeline fill / drain of only ~21 tiles; here a turn is ~7 tiles per CTA and the reduction latency is hidden behind the
-// other chains' turns.  (A single chain has nothing to hide behind and keeps the exclusive kernel.)
-// =====================================================================================================================
-constexpr int MB_IL_MAX = 4;
-constexpr int WS_BAR_E = 12;
-
-struct IlGeom { int sl_begin, sl_end, S, sgroup, e_local, e_per_warp; };
-__device__ __forceinline__ IlGeom il_geom(int np1, int y, int gy) {
-    IlGeom g;
-    const int per = (np1 + gy - 1) / gy;
-    g.sl_begin = y * per < np1 ? y * per : np1;
-    g.sl_end = g.sl_begin + per < np1 ? g.sl_begin + per : np1;
-    int Sl = 1;
-    while (Sl < gy && Sl < 32) Sl <<= 1;
-    const int lane = threadIdx.x & 31;
-    g.S = Sl; g.sgroup = lane & (Sl - 1); g.e_local = lane / Sl; g.e_per_warp = 32 / Sl;
-    return g;
-}
-// slice owner: CTA-ordered sum of chain c's level-1 cells of step seq s1 -> level-2 cells (seq s2)
-__device__ __forceinline__ void il_gather(const MbParams& P, int c, int np1, int y, int gy, uint32_t s1, uint32_t s2) {
-    const IlGeom g = il_geom(np1, y, gy);
-    const int warp = threadIdx.x >> 5;
-    const uint2* chain1 = P.cells1 + (int64_t)c * gy * P.stride;
-    const int64_t off2 = (int64_t)c * P.stride;
-    for (int base = g.sl_begin + warp * g.e_per_warp; base < g.sl_end; base += WS_WARPS * g.e_per_warp) {
-        const int i = base + g.e_local;
-        float s = 0.f;
-        if (i < g.sl_end) {
-            for (int yy = g.sgroup; yy < gy; yy += g.S)
-                s += __uint_as_float(poll_cell(chain1 + (int64_t)yy * P.stride + i, s1, P.comm.error).x);
-        }
-        for (int o = 1; o < g.S; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (i < g.sl_end && g.sgroup == 0) comm_push(P.comm, off2 + i, s, s2);
-    }
-}
-// SGD step of chain c from its level-2 cells into the shared-memory copy `sw`
-__device__ __forceinline__ void il_apply(const MbParams& P, int c, int np, float* sw, uint32_t s2, float coef, bool first_epoch,
-                                         float loss_coef, float& loss_acc) {
-    const int64_t off2 = (int64_t)c * P.stride;
-    for (int i = threadIdx.x; i <= np; i += WS_THREADS) {
-        const float tot = comm_wait_total(P.comm, off2 + i, s2);
-        if (i < np) sw[i] = sw[i] - coef * tot;
-        else if (first_epoch) loss_acc += loss_coef * tot;
-    }
-}
-
-// one turn = chain c at step s; `producer` selects the role's half of the sweep (compile-time per call site)
-template <int NA, int DIN, bool PRODUCER>
-__device__ __forceinline__ void il_turn(const MbParams& P, WsShared S, int c, int s, int y, int gy, int nb, uint32_t& nbase,
-                                        uint32_t& mph, float& loss_acc) {
-    constexpr int NP = param_count(DIN, 1);
-    const MbChain& ch = P.chains[c];
-    const int warp = threadIdx.x >> 5;
-    const float world = (float)P.comm.world;
-    S.sw = S.sw + c * WS_SLOT;
-    auto rows_of_step = [&](int st) {
-        const int b = st % nb;
-        const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
-        return (int64_t)cnt * P.rows.n_envs;
-    };
-    if (s > 0) {                                                      // the chain's previous step, reduced two turns ago
-        const float coef = ch.lr * 2.0f / ((float)rows_of_step(s - 1) * world);
-        il_apply(P, c, NP, S.sw, P.comm.seq + (uint32_t)(s - 1), coef, (s - 1) < nb, ch.loss_coef, loss_acc);
-        named_barrier(WS_BAR_E, WS_THREADS);
-    }
-    ws_build_operands<DIN>(S);
-    named_barrier(WS_BAR_C, WS_THREADS);
-    tmem_fence_after_sync();
-    rcmarl_rows Rw = P.rows;
-    Rw.n_rows = rows_of_step(s);
-    Rw.time_idx = ch.time_idx + (int64_t)(s / nb) * P.n_times + (int64_t)(s % nb) * P.mb_times;
-    const int nq = ws_tile_count(Rw.n_rows, y, gy);
-    if constexpr (PRODUCER) {
-        rcmarl_grad_job gj;
-        gj.w = ch.w; gj.target = ch.target; gj.sums = nullptr; gj.time_idx = nullptr;
-        gj.target_stride = ch.target_stride; gj.kind = ch.kind; gj.action_agent = 0;
-        float g3[HID + 1];
-#pragma unroll
-        for (int k = 0; k <= HID; ++k) g3[k] = 0.f;
-        float loss = 0.f;
-        ws_produce<NA, DIN, WS_SHADOW_STEP>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss);
-        named_barrier(WS_BAR_A, WS_THREADS);
-        ws_park_producer(S, g3, loss);
-    } else {
-        const int cw = warp - 4 * WS_GROUPS;
-        f2 acc[WS_ACC];
-#pragma unroll
-        for (int k = 0; k < WS_ACC; ++k) acc[k] = pack2(0.f, 0.f);
-        ws_consume(S, cw, nq, nbase, acc);
-        named_barrier(WS_BAR_A, WS_THREADS);
-        ws_park_consumer(S, cw, acc);
-    }
-    named_barrier(WS_BAR_B, WS_THREADS);
-    uint2* my1 = P.cells1 + ((int64_t)c * gy + y) * P.stride;
-    const uint32_t s1 = P.seq1 + (uint32_t)s;
-    ws_cta_sums<DIN>(S, [my1, s1](int i, float v) { st_cell(my1 + i, v, s1); });
-}
-
-template <int NA, bool PRODUCER>
-__device__ __forceinline__ void il_role(const MbParams& P, const WsShared& S, int y, int gy) {
-    const int n = P.n_chains;
-    const int nb = (P.n_times + P.mb_times - 1) / P.mb_times;
-    const int steps = P.epochs * nb;
-    uint32_t nbase = 0, mph = 0;
-    float loss_acc[MB_IL_MAX];
-#pragma unroll
-    for (int c = 0; c < MB_IL_MAX; ++c) loss_acc[c] = 0.f;
-    int pc = -1, ps = -1;                                             // previous turn (its level-1 cells are gathered now)
-    for (int s = 0; s < steps; ++s) {
-#pragma unroll 1
-        for (int c = 0; c < n; ++c) {
-            if (P.chains[c].kind == RCMARL_IN_SA) il_turn<NA, 3 * NA, PRODUCER>(P, S, c, s, y, gy, nb, nbase, mph, loss_acc[c]);
-            else il_turn<NA, 2 * NA, PRODUCER>(P, S, c, s, y, gy, nb, nbase, mph, loss_acc[c]);
-            if (pc >= 0) {
-                const int np1 = param_count(P.chains[pc].kind == RCMARL_IN_SA ? 3 * NA : 2 * NA, 1) + 1;
-                il_gather(P, pc, np1, y, gy, P.seq1 + (uint32_t)ps, P.comm.seq + (uint32_t)ps);
-            }
-            pc = c; ps = s;
-            named_barrier(WS_BAR_D, WS_THREADS);                      // scratch (tile buffers) reusable
-        }
-    }
-    // epilogue: the last turn's gather, then every chain's last step
-    {
-        const int np1 = param_count(P.chains[pc].kind == RCMARL_IN_SA ? 3 * NA : 2 * NA, 1) + 1;
-        il_gather(P, pc, np1, y, gy, P.seq1 + (uint32_t)ps, P.comm.seq + (uint32_t)ps);
-    }
-#pragma unroll 1
-    for (int c = 0; c < n; ++c) {
-        const MbChain& ch = P.chains[c];
-        const int np = param_count(ch.kind == RCMARL_IN_SA ? 3 * NA : 2 * NA, 1);
-        const int b = (steps - 1) % nb;
-        const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
-        const float coef = ch.lr * 2.0f / ((float)((int64_t)cnt * P.rows.n_envs) * (float)P.comm.world);
-        float* sw = S.sw + c * WS_SLOT;
-        il_apply(P, c, np, sw, P.comm.seq + (uint32_t)(steps - 1), coef, (steps - 1) < nb, ch.loss_coef, loss_acc[c]);
-        named_barrier(WS_BAR_E, WS_THREADS);
-        if (y == 0) {
-            for (int i = threadIdx.x; i < np; i += WS_THREADS) ch.w[i] = sw[i];
-            if (threadIdx.x == (np % WS_THREADS) && ch.loss_out)
-                *ch.loss_out = ch.loss_accumulate ? *ch.loss_out + loss_acc[c] : loss_acc[c];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(WS_THREADS, 1) mb_persist_il_kernel(const __grid_constant__ MbParams P) {
-    extern __shared__ __align__(16) float smem[];
-    pdl_launch_dependents();
-    const int y = blockIdx.x, gy = gridDim.x, warp = threadIdx.x >> 5;
-    const WsShared S = ws_carve(smem, MB_IL_MAX);
-    ws_init(S);
-    pdl_wait();
-    for (int c = 0; c < P.n_chains; ++c)
-        stage_weights(S.sw + c * WS_SLOT, P.chains[c].w, param_count(P.chains[c].kind == RCMARL_IN_SA ? 15 : 10, 1));
-    __syncthreads();
-    if (warp < 4 * WS_GROUPS) il_role<5, true>(P, S, y, gy);
-    else il_role<5, false>(P, S, y, gy);
-    tmem_fence_before_sync();
-    named_barrier(WS_BAR_C, WS_THREADS);
-    if (warp == 0) tmem_dealloc_all(*S.tslot);
-}
 #endif  // RCMARL_GRAD_WS
 
 }  // namespace rcmarl

@@ -662,33 +662,6 @@ static int launch_mb_persist_ws(const MbParams& P, int n_ctas, cudaStream_t st) 
 }
 #endif
 
-#if RCMARL_GRAD_WS
-static int launch_mb_persist_il(const MbParams& P, int n_ctas, cudaStream_t st) {
-    constexpr size_t smem = sizeof(float) * ws_smem_floats(MB_IL_MAX);
-    static_assert(smem <= 227 * 1024, "mb_persist_il_kernel exceeds the shared-memory limit");
-    static int resident = -1;
-    if (resident < 0) {
-        if (set_smem(mb_persist_il_kernel, smem)) return RCMARL_ERR_CUDA;
-        int per_sm = 0;
-        RC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_persist_il_kernel, WS_THREADS, smem));
-        resident = per_sm * sm_count_cached();
-    }
-    if (n_ctas > resident) return RCMARL_ERR_ARG;
-    cudaLaunchAttribute pdl;
-    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl.val.programmaticStreamSerializationAllowed = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_ctas);
-    cfg.blockDim = dim3(WS_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cfg.attrs = &pdl;
-    cfg.numAttrs = 1;
-    RC_CUDA(cudaLaunchKernelEx(&cfg, mb_persist_il_kernel, P));
-    RC_CUDA(cudaGetLastError());
-    return 0;
-}
-#endif
 
 template <int NA>
 static int launch_mb_persist(const MbParams& P, int n_ctas, cudaStream_t st) {
@@ -885,7 +858,7 @@ int rcmarl_minibatch_sgd(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
 int64_t rcmarl_minibatch_cells_bytes(int n_jobs, int max_params) {
     if (n_jobs < 1) n_jobs = 1;
     // level 1: one row of cells per CTA (<= SMs); level 2 (single GPU): 2 slots x n_jobs rows; + the error word
-    // (interleaved mode: every CTA holds a row per chain)
+    // (sized generously: a row per CTA AND chain)
     return ((int64_t)sm_count_cached() * (int64_t)n_jobs + 2 * (int64_t)n_jobs) * (int64_t)(max_params + 1) * (int64_t)sizeof(uint2) + 64;
 }
 
@@ -931,22 +904,11 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
     }
     const int cpc = NA == 5 ? grad_chunks_per_cta<5>(RCMARL_LOSS_MSE) : grad_chunks_per_cta<16>(RCMARL_LOSS_MSE);
     const int64_t n_rows_mb = (int64_t)(n_times < mb_times ? n_times : mb_times) * rows->n_envs;
-    bool interleaved = false;
-#if RCMARL_GRAD_WS
-    {   // 2 .. MB_IL_MAX chains of a 5-agent team: every CTA serves every chain in turn (RCMARL_MB_INTERLEAVE=0: exclusive shares)
-        static int il = -1;
-        if (il < 0) { const char* e = getenv("RCMARL_MB_INTERLEAVE"); il = e ? (e[0] != '0') : 0; }
-        interleaved = il && NA == 5 && n_jobs >= 2 && n_jobs <= MB_IL_MAX;
-    }
-#endif
+    // CTA shares by cost (the chains do not share rows in L2 the way the lock-step full-batch jobs do).  A mapping with every
+    // CTA serving every chain in turn (reduction of a chain hidden behind the other chains' turns) measured 70 instead of 46 us
+    // per step and was removed (profiles/r02_kernel_experiments.md).
     int n_ctas = 0;
-    if (interleaved) {
-        const int64_t tiles = (n_rows_mb + 127) / 128;
-        n_ctas = (int)(tiles < sm_count_cached() ? tiles : sm_count_cached());
-        if (n_ctas < 1) n_ctas = 1;
-        for (int j = 0; j <= n_jobs; ++j) P.cta_first[j] = 0;
-    } else {
-        // CTA shares by cost (the chains do not share rows in L2 the way the lock-step full-batch jobs do)
+    {
         int g[RCMARL_MAX_JOBS];
         plan_shares(n_jobs, cost, (n_rows_mb + 63) / 64, cpc, sm_count_cached(), true, g);
         for (int j = 0; j < n_jobs; ++j) { P.cta_first[j] = (int16_t)n_ctas; n_ctas += g[j]; }
@@ -955,7 +917,7 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
     P.n_chains = n_jobs; P.epochs = epochs; P.n_times = n_times; P.mb_times = mb_times; P.stride = maxn;
     const int64_t steps = rcmarl_minibatch_steps(epochs, n_times, mb_times);
     if ((uint64_t)seq_first + (uint64_t)steps >= 0xFFFFFFFFull) return RCMARL_ERR_ARG;
-    const int64_t l1 = (int64_t)n_ctas * maxn * (interleaved ? n_jobs : 1), l2 = 2 * (int64_t)n_jobs * maxn;
+    const int64_t l1 = (int64_t)n_ctas * maxn, l2 = 2 * (int64_t)n_jobs * maxn;
     if ((l1 + l2) * (int64_t)sizeof(uint2) + 64 > cells_bytes) return RCMARL_ERR_WORKSPACE;
     if (((uintptr_t)cells & 15) != 0) return RCMARL_ERR_ARG;
     P.cells1 = (uint2*)cells;
@@ -971,7 +933,6 @@ int rcmarl_minibatch_fit(const rcmarl_rows* rows, const rcmarl_grad_job* gjobs, 
     }
     cudaStream_t st = (cudaStream_t)stream;
 #if RCMARL_GRAD_WS
-    if (interleaved) return launch_mb_persist_il(P, n_ctas, st);
     if (NA == 5) return launch_mb_persist_ws(P, n_ctas, st);
 #endif
     return NA == 5 ? launch_mb_persist<5>(P, n_ctas, st) : launch_mb_persist<16>(P, n_ctas, st);

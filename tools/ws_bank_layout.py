@@ -37,27 +37,42 @@ def lm_cur(lane):
 def lm_grpfast(lane):
     if lane>=30: return (0,0)
     return (lane//3, lane%3)
-cur_a=[0,2,4,6,8]; cur_d={(0,0):10,(0,1):13,(1,0):16,(1,1):19}
-print("current", cost(23,cur_a,cur_d,lm_cur), "ideal", 5*4)
-best=None
-for lmname,lm in (("cur",lm_cur),("grpfast",lm_grpfast)):
-  for S in (23,25):
-    # place 9 regions + pads in S units: order permutations of regions with pad positions
-    regs=[('a',0,2),('a',1,2),('a',2,2),('a',3,2),('a',4,2),('d',(0,0),3),('d',(0,1),3),('d',(1,0),3),('d',(1,1),3)]
-    npad=S-22
-    random.seed(1)
-    for trial in range(200000):
-        order=regs[:]; random.shuffle(order)
-        # insert pads at random gaps
-        gaps=[0]*(len(order)+1)
-        for _ in range(npad): gaps[random.randrange(len(order)+1)]+=1
-        pos=0; aoff=[0]*5; doff={}
-        for i,r in enumerate(order):
-            pos+=gaps[i]
-            if r[0]=='a': aoff[r[1]]=pos
-            else: doff[r[1]]=pos
-            pos+=r[2]
-        c=cost(S,aoff,doff,lm)
-        if best is None or c<best[0]:
-            best=(c,lmname,S,aoff[:],dict(doff)); print(best)
-            if c==20: break
+
+
+def header_layout(path):
+    """(a-tile unit offsets, delta-half unit offsets) of the constants WS_A0..WS_A4, WS_D1A/B, WS_D2A/B in grad_kernel_ws.cuh"""
+    import re
+    txt = open(path).read()
+    val = lambda name: int(re.search(r"\b" + name + r" = (\d+)", txt).group(1))
+    for n in ("WS_A0", "WS_A1", "WS_A2", "WS_A3", "WS_A4", "WS_D1A", "WS_D1B", "WS_D2A", "WS_D2B"):
+        assert val(n) % 4 == 0, n
+    aoff = [val(f"WS_A{i}") // 4 for i in range(5)]
+    doff = {(0, 0): val("WS_D1A") // 4, (0, 1): val("WS_D1B") // 4, (1, 0): val("WS_D2A") // 4, (1, 1): val("WS_D2B") // 4}
+    return val("WS_ROWF") // 4, aoff, doff
+
+
+if __name__ == "__main__":
+    cur_a=[0,2,4,6,8]; cur_d={(0,0):10,(0,1):13,(1,0):16,(1,1):19}
+    print("current", cost(23,cur_a,cur_d,lm_cur), "ideal", 5*4)
+    best=None
+    for lmname,lm in (("cur",lm_cur),("grpfast",lm_grpfast)):
+      for S in (23,25):
+        # place 9 regions + pads in S units: order permutations of regions with pad positions
+        regs=[('a',0,2),('a',1,2),('a',2,2),('a',3,2),('a',4,2),('d',(0,0),3),('d',(0,1),3),('d',(1,0),3),('d',(1,1),3)]
+        npad=S-22
+        random.seed(1)
+        for trial in range(200000):
+            order=regs[:]; random.shuffle(order)
+            # insert pads at random gaps
+            gaps=[0]*(len(order)+1)
+            for _ in range(npad): gaps[random.randrange(len(order)+1)]+=1
+            pos=0; aoff=[0]*5; doff={}
+            for i,r in enumerate(order):
+                pos+=gaps[i]
+                if r[0]=='a': aoff[r[1]]=pos
+                else: doff[r[1]]=pos
+                pos+=r[2]
+            c=cost(S,aoff,doff,lm)
+            if best is None or c<best[0]:
+                best=(c,lmname,S,aoff[:],dict(doff)); print(best)
+                if c==20: break
