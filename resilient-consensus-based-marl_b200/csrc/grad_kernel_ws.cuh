@@ -158,7 +158,7 @@ __device__ __forceinline__ void ws_store_operand(uint32_t tlane, int col_hi, int
 
 constexpr int ws_smem_floats(int n_slots = 1) {
     // packed net(s) | alignment slack | B operands (hi + lo of 32x16, 32x24, 32x24) | tile buffers | barriers + tmem slot
-    return n_slots * round32(param_count(15, 1)) + 32 + 2 * TC_N * 16 + 4 * TC_N * 24 + WS_NBUF * WS_TILE_ROWS * WS_ROWF + 64;
+    return n_slots * round32(param_count(15, 1)) + 32 + 2 * TC_N * 16 + 4 * TC_N * 24 + WS_NBUF * WS_TILE_ROWS * WS_ROWF + 256;
 }
 
 // packed-parameter index of element (ii, j) of consumer tile t (a rows 8 t .. 8 t + 7 of [x | 1] for t < 2, of [h1 | 1] else)
@@ -237,7 +237,7 @@ __device__ __forceinline__ void ws_fetch(const rcmarl_rows& Rw, const rcmarl_gra
 
 // ---- shared-memory layout (the same for both nets: the parameter region is sized for the larger one) ----
 struct WsShared {
-    float *sw, *b1h, *b1l, *b2h, *b2l, *b3h, *b3l, *bufs;
+    float *sw, *b1h, *b1l, *b2h, *b2l, *b3h, *b3l, *bufs, *red3p;
     uint64_t *full, *empty, *mma_bar;
     uint32_t* tslot;
 };
@@ -261,6 +261,7 @@ __device__ __forceinline__ WsShared ws_carve(float* smem, int n_slots = 1) {
     S.empty = bars + WS_NBUF;                                         // [WS_NBUF]  consumer team -> producers (WS_TEAM arrivals)
     S.mma_bar = bars + 2 * WS_NBUF;                                   // [WS_GROUPS]
     S.tslot = reinterpret_cast<uint32_t*>(bars + 2 * WS_NBUF + WS_GROUPS);
+    S.red3p = reinterpret_cast<float*>(bars) + 32;                    // [8 producer warps][HID + 2]: their parked sums (own region)
     return S;
 }
 // barriers + tensor memory; touches no global memory (may run before pdl_wait)
@@ -563,16 +564,19 @@ __device__ __forceinline__ void ws_consume(const WsShared& S, int cw, int nq, ui
     }
 }
 
-// ---- end of a sweep: every thread passes (A), the roles park their sums in the (now idle) tile buffers, (B), and the CTA
-// adds them up in a fixed order; store(i, v) receives the sums for the packed parameters i = 0 .. NP-1 and the loss as NP ----
+// ---- end of a sweep.  Producers park their sums in a region of their own as soon as their tiles are produced.  Consumers wait
+// for ALL consumers (a 256-thread named barrier inside the consumer branch: the other team may still be reading the buffers
+// that the scratch overlays), then park theirs in the idle tile buffers.  The CTA-wide barrier that follows sits BEHIND the
+// role branch, at one program location; store(i, v) receives the sums for the packed parameters i = 0 .. NP-1, the loss as NP ----
 __device__ __forceinline__ float* ws_red(const WsShared& S) { return S.bufs; }
 // floats per parked consumer lane: 80 sums + 4 pad = 21 x 16 bytes (odd), so the lanes' STS.128 spread over the bank groups
 // (at 80 floats the eight lanes of a quarter-warp hit two bank groups: 4-way conflicts on every store of the epilogue)
 constexpr int WS_PARK = 2 * WS_ACC + 4;
-__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.bufs + WS_CONS * 32 * WS_PARK; }
+__device__ __forceinline__ float* ws_red3(const WsShared& S) { return S.red3p; }
 __device__ __forceinline__ void ws_park_producer(const WsShared& S, const float (&g3)[HID + 1], float loss) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* red3 = ws_red3(S);
+    named_barrier(1 + (warp >> 2), 128);      // the group is through with its tiles (and its warps are converged for the shuffles)
     loss = warp_sum(loss);
     if (lane == 0) red3[warp * (HID + 2) + HID + 1] = loss;
 #pragma unroll
@@ -621,7 +625,7 @@ __device__ __forceinline__ void ws_cta_sums(const WsShared& S, ST store) {
         store(NP, s);
     }
 }
-constexpr int WS_BAR_A = 8, WS_BAR_B = 9, WS_BAR_C = 10, WS_BAR_D = 11;             // CTA-wide named barriers (both roles, any code location)
+constexpr int WS_BAR_CONS = 8;                                // named barrier of the 8 consumer warps (after their last tile)
 
 // =====================================================================================================================
 // one-shot kernel (rcmarl_grad): one sweep, sums to the CTA's partial slot
@@ -650,7 +654,6 @@ __device__ __forceinline__ void ws_body(const GradParams& P, const rcmarl_grad_j
         for (int j = 0; j <= HID; ++j) g3[j] = 0.f;
         float loss = 0.f;
         ws_produce<NA, DIN, WS_SHADOW_SWEEP>(S, Rw, job, y, gy, nq, nbase, mph, g3, loss);
-        named_barrier(WS_BAR_A, WS_THREADS);                          // every tile produced and consumed
         ws_park_producer(S, g3, loss);
     } else {
         const int cw = warp - 4 * WS_GROUPS;
@@ -659,7 +662,7 @@ __device__ __forceinline__ void ws_body(const GradParams& P, const rcmarl_grad_j
         for (int e = 0; e < WS_ACC; ++e) acc[e] = pack2(0.f, 0.f);
         uint32_t nbase = 0;
         ws_consume(S, cw, nq, nbase, acc);
-        named_barrier(WS_BAR_A, WS_THREADS);
+        named_barrier(WS_BAR_CONS, 32 * WS_CONS);                     // every tile consumed
         ws_park_consumer(S, cw, acc);
     }
 #if RCMARL_PDL_REDUCE

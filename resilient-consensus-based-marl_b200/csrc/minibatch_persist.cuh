@@ -156,8 +156,7 @@ mb_persist_kernel(const __grid_constant__ MbParams P) {
 #if RCMARL_GRAD_WS
 // =====================================================================================================================
 // The same persistent fit on the warp-specialised tensor-core core (grad_kernel_ws.cuh), n_agents = 5.  Both roles run the
-// whole step loop inside their own branch (the register budgets of producers and consumers differ after setmaxnreg, so
-// there is no common code after the split); CTA-wide points are named barriers that both roles reach.
+// same step loop with the role branch inside the step; every CTA-wide barrier sits behind that branch (one program location).
 // =====================================================================================================================
 struct MbStepCtx {
     uint2* my1;                 // this CTA's level-1 cells
@@ -229,46 +228,50 @@ __device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch,
     uint32_t seq1 = P.seq1, seq2 = P.comm.seq, nbase = 0;      // nbase: this stream's tiles so far (ring bookkeeping)
     float loss_acc = 0.f;
 
-    if (warp < 4 * WS_GROUPS) {
-        uint32_t mph = 0;
+    // One step loop for both roles: the role branch sits INSIDE the step, every CTA-wide barrier behind it at one program
+    // location (nothing role-specific is live there: both roles have parked their sums by then).
+    const bool producer = warp < 4 * WS_GROUPS;
+    const int cw = warp - 4 * WS_GROUPS;
+    const int group = warp >> 2, prow = (warp & 3) * 32 + lane;      // producer group, row of the tile
+    uint32_t mph = 0;
 #if RCMARL_WS_TIMELINE
-        const bool mb_tl_on = blockIdx.x == 0 && threadIdx.x == 0;
-        int mb_tl_step = -1;
+    const bool mb_tl_on = blockIdx.x == 0 && threadIdx.x == 0;       // ticks 0 .. 9: first producer thread
+    int mb_tl_step = -1;
 #else
-        constexpr bool mb_tl_on = false;
-        constexpr int mb_tl_step = 0;
+    constexpr bool mb_tl_on = false;
+    constexpr int mb_tl_step = 0;
 #endif
-        const int group = warp >> 2, prow = (warp & 3) * 32 + lane;  // producer group, row of the tile
-        // rows of step (e, b): a mini-batch is mb_times time rows x all environments of this rank
-        auto step_rows = [&](int e, int b, rcmarl_rows& R) {
-            const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
-            R.n_rows = (int64_t)cnt * R.n_envs;
-            R.time_idx = ch.time_idx + (int64_t)e * P.n_times + (int64_t)b * P.mb_times;
-        };
-        WsFirst<DIN> nf;                                              // first tile of the NEXT sweep, fetched one step ahead
-        nf.tgt = 0.f; nf.live = false;
+    // rows of step (e, b): a mini-batch is mb_times time rows x all environments of this rank
+    auto step_rows = [&](int e, int b, rcmarl_rows& R) {
+        const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
+        R.n_rows = (int64_t)cnt * R.n_envs;
+        R.time_idx = ch.time_idx + (int64_t)e * P.n_times + (int64_t)b * P.mb_times;
+    };
+    WsFirst<DIN> nf;                                                  // first tile of the NEXT sweep, fetched one step ahead
+    nf.tgt = 0.f; nf.live = false;
 #pragma unroll
-        for (int k = 0; k < DIN; ++k) nf.x[k] = 0.f;
-        step_rows(0, 0, Rw);
-        if (group < ws_tile_count(Rw.n_rows, y, gy)) ws_fetch<NA, DIN>(Rw, gj, y, gy, group, prow, nf.x, nf.tgt, nf.live);
-        for (int e = 0; e < P.epochs; ++e) {
-            for (int b = 0; b < nb; ++b, ++seq1, ++seq2) {
+    for (int k = 0; k < DIN; ++k) nf.x[k] = 0.f;
+    step_rows(0, 0, Rw);
+    if (producer && group < ws_tile_count(Rw.n_rows, y, gy)) ws_fetch<NA, DIN>(Rw, gj, y, gy, group, prow, nf.x, nf.tgt, nf.live);
+    for (int e = 0; e < P.epochs; ++e) {
+        for (int b = 0; b < nb; ++b, ++seq1, ++seq2) {
 #if RCMARL_WS_TIMELINE
-                ++mb_tl_step;
+            ++mb_tl_step;
 #endif
-                MB_TICK(0);
-                ws_build_operands<DIN>(S);
-                named_barrier(WS_BAR_C, WS_THREADS);
-                MB_TICK(1);
-                tmem_fence_after_sync();
-                step_rows(e, b, Rw);
-                const int nq = ws_tile_count(Rw.n_rows, y, gy);
+            MB_TICK(0);
+            ws_build_operands<DIN>(S);
+            __syncthreads();
+            MB_TICK(1);
+            tmem_fence_after_sync();
+            step_rows(e, b, Rw);
+            const int nq = ws_tile_count(Rw.n_rows, y, gy);
+            const float n_rows_f = (float)Rw.n_rows;
+            if (producer) {
                 float g3[HID + 1];
 #pragma unroll
                 for (int k = 0; k <= HID; ++k) g3[k] = 0.f;
                 float loss = 0.f;
                 ws_produce<NA, DIN, WS_SHADOW_STEP, true>(S, Rw, gj, y, gy, nq, nbase, mph, g3, loss, &nf);
-                const float n_rows_f = (float)Rw.n_rows;
                 {   // the next step's first rows: in flight during this step's reduction, exchange and SGD
                     const int bn = b + 1 < nb ? b + 1 : 0, en = b + 1 < nb ? e : e + 1;
                     if (en < P.epochs) {
@@ -278,47 +281,27 @@ __device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch,
                     }
                 }
                 MB_TICK(2);
-                named_barrier(WS_BAR_A, WS_THREADS);
-                MB_TICK(3);
                 ws_park_producer(S, g3, loss);
-                MB_TICK(9);
-                named_barrier(WS_BAR_B, WS_THREADS);
-                MB_TICK(4);
-                mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / (n_rows_f * world), e == 0, loss_acc, mb_tl_on, mb_tl_step);
-                named_barrier(WS_BAR_D, WS_THREADS);                  // new parameters visible; scratch reusable
-                MB_TICK(8);
-            }
-        }
-    } else {
-        const int cw = warp - 4 * WS_GROUPS;
+                MB_TICK(3);
+            } else {
 #if RCMARL_WS_TIMELINE
-        const bool mb_tl_on = blockIdx.x == 0 && threadIdx.x == 32 * 4 * WS_GROUPS;   // first consumer thread: ticks 10 .. 12
-        int mb_tl_step = -1;
+                const bool mb_tl_on = blockIdx.x == 0 && threadIdx.x == 32 * 4 * WS_GROUPS;   // first consumer thread: ticks 10 .. 12
 #endif
-        for (int e = 0; e < P.epochs; ++e) {
-            for (int b = 0; b < nb; ++b, ++seq1, ++seq2) {
-#if RCMARL_WS_TIMELINE
-                ++mb_tl_step;
-#endif
-                ws_build_operands<DIN>(S);
-                named_barrier(WS_BAR_C, WS_THREADS);
-                tmem_fence_after_sync();
-                const int cnt = P.n_times - b * P.mb_times < P.mb_times ? P.n_times - b * P.mb_times : P.mb_times;
-                Rw.n_rows = (int64_t)cnt * Rw.n_envs;
-                const int nq = ws_tile_count(Rw.n_rows, y, gy);
                 f2 acc[WS_ACC];
 #pragma unroll
                 for (int k = 0; k < WS_ACC; ++k) acc[k] = pack2(0.f, 0.f);
                 ws_consume(S, cw, nq, nbase, acc);
                 MB_TICK(10);
-                named_barrier(WS_BAR_A, WS_THREADS);
+                named_barrier(WS_BAR_CONS, 32 * WS_CONS);             // every tile consumed
                 MB_TICK(11);
                 ws_park_consumer(S, cw, acc);
                 MB_TICK(12);
-                named_barrier(WS_BAR_B, WS_THREADS);
-                mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / ((float)Rw.n_rows * world), e == 0, loss_acc);
-                named_barrier(WS_BAR_D, WS_THREADS);
             }
+            __syncthreads();                                          // scratch complete
+            MB_TICK(4);
+            mb_step_tail<DIN>(S, c, seq1, seq2, ch.lr * 2.0f / (n_rows_f * world), e == 0, loss_acc, mb_tl_on, mb_tl_step);
+            __syncthreads();                                          // new parameters visible; scratch reusable
+            MB_TICK(8);
         }
     }
     if (y == 0) {
@@ -326,7 +309,7 @@ __device__ __forceinline__ void mb_body_ws(const MbParams& P, const MbChain& ch,
         if (threadIdx.x == (NP % WS_THREADS) && ch.loss_out) *ch.loss_out = ch.loss_accumulate ? *ch.loss_out + loss_acc : loss_acc;
     }
     tmem_fence_before_sync();
-    named_barrier(WS_BAR_C, WS_THREADS);
+    __syncthreads();
     if (warp == 0) tmem_dealloc_all(*S.tslot);
 }
 
