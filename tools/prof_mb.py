@@ -40,10 +40,10 @@ if os.environ.get("RCMARL_MB_TIMELINE") == "1":            # debug build (make v
     lib.rcmarl_debug_timeline_mb.restype = C.c_int
     st = lib.rcmarl_debug_timeline_mb(buf, 64 * 16)
     T = np.array(buf[:], np.int64).reshape(64, 16)[8:60]
-    order = [0, 1, 2, 3, 9, 4, 5, 6, 7, 8]                   # producer thread 0 (tick 9 sits between 3 and 4)
-    names = ["operand rebuild + barrier", "own tiles produced (sweep) + next step's first loads issued", "barrier A (all tiles consumed)",
-             "park (warp sums of the output-layer gradient)", "barrier B", "CTA sums -> level-1 cells",
-             "gather (poll level-1, publish level-2)", "apply (poll level-2, SGD)", "barrier D"]
+    order = [0, 1, 2, 3, 4, 5, 6, 7, 8]                      # producer thread 0
+    names = ["operand rebuild + barrier", "own tiles produced (sweep) + next step's first loads issued",
+             "park (warp sums of the output-layer gradient)", "CTA barrier (consumers' last tile + their park)",
+             "CTA sums -> level-1 cells", "gather (poll level-1, publish level-2)", "apply (poll level-2, SGD)", "closing barrier"]
     t = T[:, order]
     d = np.diff(t, axis=1)
     per = np.diff(T[:, 0])
@@ -51,7 +51,7 @@ if os.environ.get("RCMARL_MB_TIMELINE") == "1":            # debug build (make v
     for k, n in enumerate(names):
         print(f"{n:62s} mean {d[:, k].mean():8.0f}  min {d[:, k].min():6d}  max {d[:, k].max():6d}")
     c = T[:, [1, 10, 11, 12]]                                # first consumer thread, relative to the producer's tick 1
-    for n, a, b in (("consumer: last tile consumed, after the operands barrier", 0, 1), ("consumer: wait at barrier A", 1, 2),
+    for n, a, b in (("consumer: last tile consumed, after the operands barrier", 0, 1), ("consumer: wait at the consumers' barrier", 1, 2),
                     ("consumer: park", 2, 3)):
         v = c[:, b] - c[:, a]
         print(f"{n:62s} mean {v.mean():8.0f}  min {v.min():6d}  max {v.max():6d}")
