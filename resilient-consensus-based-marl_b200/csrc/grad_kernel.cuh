@@ -3,7 +3,7 @@
 // agents/resilient_CAC_agents.py:99,118,136 and adversarial:41,116,133,150,163).
 //
 // The kernel is FP32-FMA work fed from shared memory, and on B200 the shared-memory pipe (one wavefront per
-// clock per SM) is the first limit: measured with ncu (profiles/r01_grad_v1_ncu.md) a warp-uniform LDS.128 costs
+// clock per SM) is the first limit: measured with ncu (profiles/r01_grad_kernel_ncu.md) a warp-uniform LDS.128 costs
 // 2 wavefronts and any other LDS.128 costs 4, while the four FMA pipes retire 4 warp-FFMAs per clock.  Balance
 // therefore needs >= 4 FFMA per wavefront everywhere:
 //   phase 1 (forward + backward-data): every lane carries R = 2 buffer rows, so each broadcast weight quad
